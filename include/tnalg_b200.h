@@ -1,0 +1,184 @@
+/*
+ * tnalg_b200 -- C ABI of the B200 (sm_100a) finite-size DMRG hot path of ranshiju/T-Nalg.
+ *
+ * The reference is pure Python and has no FFI: the seam this ABI replaces is the set of numpy/scipy call
+ * sites inside MPSClass.MpsOpenBoundaryClass and TensorBasicModule.  Each entry point
+ * cites the reference interface it stands in for (file:line relative to the reference tree).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative tn_status on failure; tn_last_error() gives the text
+ *     (thread-local).  Shape / alignment / null-pointer mistakes are errors, never undefined behaviour.
+ *   - all `double*` arguments marked [dev] are device pointers to C-contiguous (row-major) float64;
+ *     [host] arguments are ordinary host memory read before the call returns.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are asynchronous with
+ *     respect to the host unless stated otherwise.
+ *   - no hidden device allocation: scratch is passed by the caller; *_workspace_bytes() says how much.
+ *   - MPS tensors are (a, d, b) = (left bond, physical, right bond), flattened in C order -- the layout of
+ *     mps[n] in MPSClass.py:66-72.  Environment matrices are indexed [bra, ket] and act as E . psi
+ *     (MPSClass.py:757-775 passes E.T to absorb_matrix2tensor, which contracts the first index).
+ */
+#ifndef TNALG_B200_H
+#define TNALG_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TN_MAX_PHYS_DIM 3 /* d = 2 (spin-1/2) and d = 3 (spin-1), Parameters.py:440-446 */
+
+typedef enum {
+  TN_OK = 0,
+  TN_ERR_INVALID = -1,   /* bad argument (shape, null pointer, alignment) */
+  TN_ERR_CUDA = -2,      /* CUDA runtime error, text in tn_last_error() */
+  TN_ERR_WORKSPACE = -3, /* workspace too small */
+  TN_ERR_NOCONV = -4,    /* iteration limit reached (result is still written) */
+  TN_ERR_DEVICE = -5     /* not an sm_100 device */
+} tn_status;
+
+const char* tn_last_error(void);
+int tn_version(void);
+/* sm_count, compute capability of the current device; fails with TN_ERR_DEVICE when it is not sm_100. */
+int tn_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* number of kernels this library has launched since tn_launch_count_reset() (bench.py "gpu_launches"). */
+long long tn_launch_count(void);
+void tn_launch_count_reset(void);
+
+/* --------------------------------------------------------------------------------------------------
+ * Chain GEMM: the FP64 tensor-core (DMMA) contraction engine every tensor-network contraction below is built
+ * from.   C_p (+)= alpha_p * sum_{l in links(p)}  opA_l(A_l) . opB_l(B_l)      for p = 0 .. n_problems-1
+ * All problems of one call share M, N, K and the leading dimensions.
+ *   mode TN_NN : A_l is (M,K) row-major, B_l is (K,N) row-major with N = d*Ny and column index (s,y); a link's
+ *                d x d operator acts on s:   B'[k,(s,y)] = sum_s' op[s,s'] B[k,(s',y)]
+ *                (E . (op T) with T an (a,d,b) tensor: absorb_matrix2tensor bonds 0+1, TensorBasicModule.py:387-424)
+ *   mode TN_NT : A_l is (M,K) row-major with M = Mx*d and row index (x,s), B_l is (N,K) row-major;
+ *                A'[(x,s),k] = sum_s' op[s,s'] A[(x,s'),k]            ((op T) . E^T, bonds 1+2)
+ *   mode TN_TN : A_l is (K,M) row-major, B_l is (K,N) row-major, no operator  (T^T . X, the closing GEMM of
+ *                bound_vec_operator_left2right, TensorBasicModule.py:560-568)
+ * A link with has_op == 0 uses the identity.  d = 1 disables the operator machinery.
+ * deterministic != 0 forbids split-K (one CTA owns each output tile, fixed summation order).
+ * Otherwise the K range of a tile may be split over CTAs (stream-K) and partial tiles are combined with FP64
+ * atomics; the result then differs between runs at the 1e-16 relative level.
+ * accumulate == 0: C is overwritten; != 0: the result is added to the existing C.
+ * -------------------------------------------------------------------------------------------------- */
+enum { TN_NN = 0, TN_NT = 1, TN_TN = 2 };
+
+typedef struct {
+  const double* A; /* [dev] */
+  const double* B; /* [dev] */
+  double op[TN_MAX_PHYS_DIM * TN_MAX_PHYS_DIM]; /* row-major d x d, used when has_op != 0 */
+  int has_op;
+  int reserved;
+} tn_link;
+
+typedef struct {
+  double* C; /* [dev] (M,N) row-major, leading dimension ldc */
+  double alpha;
+  int link_begin; /* index of the first link of this problem in the links array */
+  int link_count;
+  int accumulate;
+  int reserved;
+} tn_problem;
+
+size_t tn_chain_gemm_workspace_bytes(int n_problems, int n_links);
+int tn_chain_gemm(int mode, int M, int N, int K, int d, int lda, int ldb, int ldc,
+                  const tn_problem* problems /* [host] */, int n_problems,
+                  const tn_link* links /* [host] */, int n_links, int deterministic,
+                  void* workspace /* [dev] */, size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------------------
+ * Environment update through one site tensor (a5: bound_vec_operator_left2right / right2left,
+ * TensorBasicModule.py:530-619), batched over every operator that crosses the bond and fused with the sum over
+ * the terms that close on this site (MPSClass.py:474-530 keeps one matrix per term instead):
+ *   dir = 0 (left to right):  E_out[j][b,b'] = sum_{l in links(j)} sum conj(T[a,s,b]) E_l[a,a'] op_l[s,s'] T[a',s',b']
+ *   dir = 1 (right to left):  E_out[j][a,a'] = sum_{l in links(j)} sum conj(T[a,s,b]) E_l[b,b'] op_l[s,s'] T[a',s',b']
+ * link_E[l] == NULL means the identity (the far side of the bond is orthonormal); link_has_op[l] == 0 means the
+ * identity on the physical index.  Coefficients are folded into link_op.  Deterministic.
+ * -------------------------------------------------------------------------------------------------- */
+size_t tn_env_update_workspace_bytes(int a, int d, int b, int n_out, int n_links);
+int tn_env_update(int dir, const double* T /* [dev] (a,d,b) */, int a, int d, int b, int n_out,
+                  double* const* E_out /* [host] array of n_out [dev] pointers */,
+                  const int* out_link_begin /* [host] n_out+1 prefix offsets into the link arrays */,
+                  const double* const* link_E /* [host] n_links [dev] pointers or NULL */,
+                  const double* link_op /* [host] n_links * d*d */, const int* link_has_op /* [host] n_links */,
+                  void* workspace /* [dev] */, size_t workspace_bytes, void* stream);
+
+/* out[i] = sum_t coeffs[t] * xs[t][i]  (the sums classify_and_update_env keeps per key, MPSClass.py:684-733) */
+int tn_lincomb(double* out /* [dev] */, long long n, int n_terms, const double* const* xs /* [host] of [dev] */,
+               const double* coeffs /* [host] */, void* stream);
+
+/* out = op (d x d, [host]) applied on the physical index of T (a,d,b): out[a,s,b] = sum_s' op[s,s'] T[a,s',b]
+ * (absorb_matrix2tensor(T, op.T, 1), TensorBasicModule.py:415-421) */
+int tn_apply_site_op(double* out /* [dev] */, const double* T /* [dev] */, int a, int d, int b,
+                     const double* op /* [host] d*d */, void* stream);
+
+/* result[0] = sum_i x[i]*y[i]; deterministic two-stage reduction; result is a [dev] double.
+ * tn_trace: result[0] = sum_i E[i,i] of an (n,n) matrix (np.trace in MPSClass.py:872,909). */
+int tn_dot(const double* x, const double* y, long long n, double* result /* [dev] */, void* workspace /* [dev] */,
+           size_t workspace_bytes, void* stream);
+size_t tn_dot_workspace_bytes(long long n);
+int tn_trace(const double* E /* [dev] (n,n) */, int n, double* result /* [dev] */, void* stream);
+
+/* --------------------------------------------------------------------------------------------------
+ * Effective-Hamiltonian plan for one site (a1/a2): the groups of MpsOpenBoundaryClass.opt_env
+ * (MPSClass.py:684-733) with every coefficient already folded in:
+ *   HL  '1_0_0' (a,a) or NULL          HR  '0_0_1' (b,b) or NULL          M  '0_s_0' summed (d,d) [host] or NULL
+ *   LS[k], ls_op[k]  '1_s_0': (LS_k (x) op_k)      RS[k], rs_op[k]  '0_s_1': (op_k (x) RS_k)
+ *   XL[i], XR[i], x_coeff[i]  '1_0_1': c_i (XL_i (x) 1 (x) XR_i)
+ * H_eff psi = HL psi + psi HR^T + M psi + sum_k LS_k op_k psi + sum_k op_k psi RS_k^T + sum_i c_i XL_i psi XR_i^T.
+ * tn_effh_matvec:  out = c_id * psi + c_h * H_eff psi ; the reference handle
+ * update_tensor_eigs_f_handle_optimized (MPSClass.py:755-776) is (c_id, c_h) = (1, -tau).
+ * Executed as two chain-GEMM launches (left stage TN_NN, right stage TN_NT) plus one element-wise init kernel;
+ * the crossing intermediates XL_i psi live in the plan workspace.
+ * rank/world shard the links round-robin (multi-GPU): the caller all-reduces `out`; the identity
+ * and on-site parts are applied on rank 0 only.
+ * -------------------------------------------------------------------------------------------------- */
+typedef struct tn_effh_plan tn_effh_plan;
+
+size_t tn_effh_plan_workspace_bytes(int a, int d, int b, int n_ls, int n_rs, int n_x);
+int tn_effh_plan_create(tn_effh_plan** plan, int a, int d, int b, const double* HL /* [dev] */,
+                        const double* HR /* [dev] */, const double* M /* [host] d*d or NULL */, int n_ls,
+                        const double* const* LS /* [host] of [dev] */, const double* ls_op /* [host] n_ls*d*d */,
+                        int n_rs, const double* const* RS, const double* rs_op, int n_x,
+                        const double* const* XL, const double* const* XR, const double* x_coeff /* [host] */,
+                        int rank, int world, void* workspace /* [dev] */, size_t workspace_bytes, void* stream);
+int tn_effh_matvec(tn_effh_plan* plan, const double* psi_in /* [dev] */, double* psi_out /* [dev] */, double c_id,
+                   double c_h, void* stream);
+/* algorithmic flop of one matvec: 2*a*d*b*[a*(K_L+n_x) + b*(K_R+n_x)], and executed flop. */
+int tn_effh_plan_flops(const tn_effh_plan* plan, double* algorithmic, double* executed);
+int tn_effh_plan_destroy(tn_effh_plan* plan);
+
+/* --------------------------------------------------------------------------------------------------
+ * Device-resident Lanczos (a8): the eigenpair of (1 - tau*H_eff) of largest magnitude, i.e. what
+ * eigsh(LinearOperator, k=1, which='LM', v0, tol) returns at MPSClass.py:801-805.  Thick-restart Lanczos on
+ * H_eff itself (same Krylov space, no 1e-4 shift cancellation) with full CGS2 re-orthogonalisation; all scalars,
+ * the projected tridiagonal eigenproblem and the convergence test stay on the device; the host reads one flag
+ * per restart cycle.  Converged when  tau*|beta_m u_m| <= tol * |1 - tau*theta|  (ARPACK's criterion applied to
+ * the shifted operator).  ncv = Krylov dimension per cycle (ARPACK default 20), max_restarts cycles at most.
+ * allreduce (may be NULL) is called once per matvec on the partial H psi when the plan is sharded.
+ * Blocking: returns after the result is available.  lambda/resid/n_matvec are [host] outputs.
+ * -------------------------------------------------------------------------------------------------- */
+typedef int (*tn_allreduce_fn)(double* buf /* [dev] */, long long count, void* user, void* stream);
+
+size_t tn_lanczos_workspace_bytes(long long n, int ncv);
+int tn_lanczos_lm1(tn_effh_plan* plan, double tau, const double* v0 /* [dev] n */, double tol, int ncv,
+                   int max_restarts, double* lambda_out, double* vec_out /* [dev] n */, int* n_matvec_out,
+                   double* resid_out, tn_allreduce_fn allreduce, void* allreduce_user, void* workspace /* [dev] */,
+                   size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------------------
+ * One-sided Jacobi SVD (a7 'svd' branch, a11, a12): A (m,n) row-major = U diag(S) Vt, singular values sorted
+ * in decreasing order, k = min(m,n) triplets of which the first k_keep are written (truncation to chi,
+ * library/MPSClass.py:186-247,1676-1686).  U is (m,k_keep), S (k_keep), Vt (k_keep,n); U or Vt may be NULL.
+ * Blocking.  sweeps_out [host] receives the number of Jacobi sweeps.
+ * -------------------------------------------------------------------------------------------------- */
+size_t tn_svd_workspace_bytes(int m, int n);
+int tn_svd_jacobi(const double* A /* [dev] */, int m, int n, int k_keep, double* U /* [dev] */, double* S /* [dev] */,
+                  double* Vt /* [dev] */, int* sweeps_out, void* workspace /* [dev] */, size_t workspace_bytes,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TNALG_B200_H */

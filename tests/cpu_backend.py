@@ -1,0 +1,179 @@
+"""Oracle-backed stand-in for tnalg_b200.ops.CudaBackend -- TEST INFRASTRUCTURE ONLY.
+
+Implements the same interface with numpy (via oracle/dmrg_oracle.py primitives) on CPU torch tensors so that the
+host logic of the product (term algebra, environment bookkeeping, sweep driver, observables, pickling) can be
+exercised by `-m "not gpu"` tests in a container without a GPU.  The product never imports this module; the
+injection point is tnalg_b200.ops.set_backend(), called from tests only.
+
+`lanczos` is a numpy transcription of the algorithm in tnalg_b200/csrc/lanczos.cu (thick restart, CGS2, ARPACK
+criterion on the shifted operator) so that its convergence behaviour is validated against the reference's results.
+"""
+import numpy as np
+import torch
+from scipy.linalg import eigh_tridiagonal
+
+from oracle import dmrg_oracle as orc
+
+
+class CpuPlan:
+    def __init__(self, shape, g):
+        self.shape = shape
+        self.g = g
+        a, d, b = shape
+        kl = (1 if g['HL'] is not None else 0) + len(g['LS'])
+        kr = (1 if g['HR'] is not None else 0) + len(g['RS'])
+        nx = len(g['XL'])
+        self.flops_algorithmic = 2.0 * a * d * b * (a * (kl + nx) + b * (kr + nx))
+        self.flops_executed = self.flops_algorithmic
+        self._handle = self
+
+    def apply(self, x):
+        g = self.g
+        t = x.reshape(self.shape)
+        out = np.zeros_like(t)
+        if g['HL'] is not None:
+            out += np.einsum('ax,xsb->asb', g['HL'], t)
+        if g['HR'] is not None:
+            out += np.einsum('asy,by->asb', t, g['HR'])
+        if g['M'] is not None:
+            out += np.einsum('st,atb->asb', g['M'], t)
+        for E, op in zip(g['LS'], g['ls_ops']):
+            out += np.einsum('ax,st,xtb->asb', E, op, t)
+        for E, op in zip(g['RS'], g['rs_ops']):
+            out += np.einsum('by,st,aty->asb', E, op, t)
+        for c, l, r in zip(g['x_coeff'], g['XL'], g['XR']):
+            out += c * np.einsum('ax,xsy,by->asb', l, t, r)
+        return out.reshape(-1)
+
+    def matvec(self, psi, c_id=0.0, c_h=1.0, out=None):
+        x = psi.numpy().reshape(-1)
+        y = c_id * x + c_h * self.apply(x)
+        return torch.from_numpy(y.reshape(psi.shape))
+
+    def destroy(self):
+        pass
+
+
+class CpuBackend:
+    name = 'cpu-oracle'
+    device = torch.device('cpu')
+    sm_count = 0
+
+    def __init__(self):
+        self.n_env_updates = 0
+        self.n_matvec = 0
+        self.last_svd_sweeps = 0
+
+    def from_numpy(self, x):
+        return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
+
+    def to_numpy(self, t):
+        return t.detach().numpy().copy()
+
+    def empty(self, *shape):
+        return torch.empty(*shape, dtype=torch.float64)
+
+    def launch_count(self):
+        return 0
+
+    def env_update(self, direction, T, outputs):
+        self.n_env_updates += 1
+        Tn = T.numpy()
+        res = []
+        fn = orc.transfer_l2r if direction == 0 else orc.transfer_r2l
+        for links in outputs:
+            acc = None
+            for E, op in links:
+                v = fn(Tn, None if op is None else np.asarray(op), None if E is None else E.numpy())
+                acc = v if acc is None else acc + v
+            res.append(torch.from_numpy(np.ascontiguousarray(acc)))
+        return res
+
+    def lincomb(self, xs, coeffs):
+        return sum(float(c) * x for c, x in zip(coeffs, xs))
+
+    def site_op(self, T, op):
+        return torch.from_numpy(np.einsum('st,atb->asb', np.asarray(op), T.numpy()))
+
+    def dot(self, x, y):
+        return torch.tensor([float((x * y).sum())], dtype=torch.float64)
+
+    def trace(self, E):
+        return torch.tensor([float(torch.trace(E))], dtype=torch.float64)
+
+    def scalars_to_host(self, slots):
+        return torch.cat(slots).numpy() if slots else np.zeros(0)
+
+    def mode_product(self, T, mat, bond):
+        return torch.from_numpy(np.ascontiguousarray(orc.mode_product(T.numpy(), mat.numpy(), bond)))
+
+    def effh_plan(self, shape, HL=None, HR=None, M=None, LS=(), ls_ops=(), RS=(), rs_ops=(), XL=(), XR=(), x_coeff=(),
+                  rank=0, world=1):
+        n = lambda t: None if t is None else t.numpy()  # noqa: E731
+        g = {'HL': n(HL), 'HR': n(HR), 'M': None if M is None else np.asarray(M), 'LS': [n(t) for t in LS],
+             'ls_ops': [np.asarray(o) for o in ls_ops], 'RS': [n(t) for t in RS], 'rs_ops': [np.asarray(o) for o in rs_ops],
+             'XL': [n(t) for t in XL], 'XR': [n(t) for t in XR], 'x_coeff': list(x_coeff)}
+        return CpuPlan(tuple(shape), g)
+
+    def lanczos(self, plan, tau, v0, tol, ncv=20, max_restarts=1000, allreduce=None):
+        """numpy transcription of tn_lanczos_lm1 (tnalg_b200/csrc/lanczos.cu)."""
+        x0 = v0.numpy().reshape(-1)
+        n = x0.size
+        m = int(min(max(ncv, 2), n, 64))
+        V = np.zeros((m + 1, n))
+        V[0] = x0 / np.linalg.norm(x0)
+        alpha, beta = np.zeros(m), np.zeros(m)
+        j0, n_mv = 0, 0
+        eps23 = 3.666852862501036e-11
+        y, lam, resid, ok = V[0], 0.0, 0.0, False
+        for cycle in range(max_restarts):
+            m_eff = m
+            for j in range(j0, m):
+                w = plan.apply(V[j])
+                n_mv += 1
+                h = V[:j + 1] @ w
+                w = w - V[:j + 1].T @ h
+                h2 = V[:j + 1] @ w
+                w = w - V[:j + 1].T @ h2
+                alpha[j] = h[j] + h2[j]
+                bj = np.linalg.norm(w)
+                beta[j] = bj
+                scale = max(abs(alpha[j]), abs(beta[j - 1]) if j > 0 else 0.0, 1e-300)
+                if bj <= 1e-14 * scale:
+                    beta[j] = 0.0
+                    m_eff = j + 1
+                    break
+                V[j + 1] = w / bj
+            breakdown = m_eff < m or beta[m_eff - 1] == 0.0
+            d, z = eigh_tridiagonal(alpha[:m_eff], beta[:m_eff - 1]) if m_eff > 1 else (alpha[:1].copy(), np.ones((1, 1)))
+            best = int(np.argmax(np.abs(1.0 - tau * d)))
+            u = z[:, best]
+            s = (0.0 if breakdown else beta[m_eff - 1]) * u[m_eff - 1]
+            theta, lam, resid = d[best], 1.0 - tau * d[best], abs(s)
+            y = u @ V[:m_eff]
+            if breakdown or abs(tau) * abs(s) <= tol * max(eps23, abs(lam)) or m >= n:
+                ok = True
+                break
+            r_hat = V[m].copy()
+            V[0], V[1] = y, r_hat
+            alpha[0], beta[0] = theta, s
+            j0 = 1
+        self.n_matvec += n_mv
+        y = y / np.linalg.norm(y)
+        return lam, torch.from_numpy(y.copy()), n_mv, resid, ok
+
+    def svd(self, A, k_keep=None):
+        u, s, vt = np.linalg.svd(A.numpy(), full_matrices=False)
+        k = s.size if k_keep is None else min(k_keep, s.size)
+        c = np.ascontiguousarray
+        return torch.from_numpy(c(u[:, :k])), torch.from_numpy(c(s[:k])), torch.from_numpy(c(vt[:k]))
+
+    def qr(self, A):
+        q, r = np.linalg.qr(A.numpy())
+        return torch.from_numpy(np.ascontiguousarray(q)), torch.from_numpy(np.ascontiguousarray(r))
+
+    def scale_diag_rows(self, S, Vt):
+        return S[:, None] * Vt
+
+    def norm(self, x):
+        return float(torch.linalg.vector_norm(x))

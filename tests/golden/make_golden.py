@@ -45,7 +45,8 @@ def pack_run(para, seed):
            'e_per_site': ob['e_per_site'], 'eb_full': ob['eb_full'], 'eb': ob['eb'], 'mx': ob['mx'],
            'mz': ob['mz'], 'corr_x': ob2['corr_x'], 'corr_z': ob2['corr_z'],
            'corr_x_stale': ob['corr_x'], 'corr_z_stale': ob['corr_z'],
-           'ent': A.ent, 'virtual_dim': A.virtual_dim, 'convergence': info['convergence']}
+           'ent': A.ent, 'virtual_dim': A.virtual_dim, 'convergence': info['convergence'],
+           'attrs': np.array(sorted(A.__dict__.keys())), 'mps_dtype': str(A.mps[0].dtype)}
     for n, lm in enumerate(A.lm):
         out['lm_%d' % n] = lm
     return out

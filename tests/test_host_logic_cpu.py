@@ -1,0 +1,178 @@
+"""Host logic of the product (term algebra, environment cache, sweep driver, observables, pickling) exercised on
+the CPU with the oracle-backed stand-in backend of tests/cpu_backend.py, against vectors produced by the
+unmodified reference (tests/golden/*.npz)."""
+import io
+import pickle
+
+import numpy as np
+import pytest
+
+from tests.cpu_backend import CpuBackend
+
+
+@pytest.fixture()
+def cpu_be():
+    from tnalg_b200 import ops
+    old = ops._backend
+    be = CpuBackend()
+    ops.set_backend(be)
+    yield be
+    ops.set_backend(old)
+
+
+def para_from_golden(g, **kw):
+    from tnalg_b200 import Parameters as Pm
+    para = dict(Pm.common_parameters_dmrg())
+    ops = [np.real(o) if np.abs(np.imag(o)).max() == 0 else o for o in g['op']]
+    para.update(lattice='arbitrary', spin='half', op=ops, index1=g['index1'], coeff1=g['coeff1'], index2=g['index2'],
+                coeff2=g['coeff2'], chi=int(g['chi']), tau=float(g['tau']), eigs_tol=float(g['eigs_tol']),
+                break_tol=float(g['break_tol']), hx=float(g['hx']), hz=float(g['hz']))
+    para.update(kw)
+    return Pm.make_consistent_parameter_dmrg(para)
+
+
+def test_parameters_match_reference_generators(golden):
+    from tnalg_b200 import Parameters as Pm
+    g = golden('e2e_chain12')
+    para = Pm.generate_parameters_dmrg('chain')
+    para.update(l=12, chi=16)
+    para = Pm.make_consistent_parameter_dmrg(para)
+    for k in ('index1', 'index2', 'coeff1', 'coeff2', 'positions_h2'):
+        assert np.array_equal(np.asarray(para[k]), g[k]), k
+    assert len(para['op']) == 7 and all(np.allclose(a, b) for a, b in zip(para['op'], g['op']))
+    assert para['data_exp'] == 'chainN12_j(1,1)_h(0,0)_chi16open' and para['d'] == 2 and para['nh'] == 33
+    g = golden('e2e_xxz10')
+    para = Pm.generate_parameters_dmrg('chain')
+    para.update(l=10, chi=12, jxy=1, jz=0.5, hx=0.3, hz=0)
+    para = Pm.make_consistent_parameter_dmrg(para)
+    for k in ('index1', 'index2', 'coeff1', 'coeff2'):
+        assert np.array_equal(np.asarray(para[k]), g[k]), k
+    assert np.allclose(para['op'][6], g['op'][6])
+    sq = Pm.generate_parameters_dmrg('square')
+    assert sq['l'] == 16 and sq['index2'].shape == (72, 4) and sq['positions_h2'].shape == (24, 2)
+
+
+@pytest.mark.parametrize('p', [0, 2, 4, 5, 8])
+def test_plan_groups_and_matvec_vs_reference(golden, cpu_be, p):
+    """the summed complementary blocks give the reference's opt_env groups and the reference's handle output"""
+    from tnalg_b200.MPSClass import MpsOpenBoundaryClass
+    g = golden('percall_j1j2')
+    L, d, chi = int(g['l']), int(g['d']), int(g['chi'])
+    ops = [np.real(o) for o in g['op']]
+    A = MpsOpenBoundaryClass(L, d, chi, operators=ops, is_save_op=True, eig_way=1)
+    for n in range(L):
+        A.mps[n] = g['p%d_mps_%d' % (p, n)]
+    A.center = p
+    env = A._environments(g['index1'], g['index2'], g['coeff1'], g['coeff2'], 1e-12)
+    # group structure == reference key set
+    kl, kr, nx = env.terms.counts(p)
+    keys = [str(k) for k in g['p%d_keys' % p]]
+    ref_left = sum(1 for k in keys if k.startswith('1_') and k.endswith('_0'))
+    ref_right = sum(1 for k in keys if k.startswith('0_') and k.endswith('_1'))
+    assert (kl, kr, nx) == (ref_left, ref_right, int(g['p%d_ncross' % p]))
+    plan = A.effective_hamiltonian_plan(p, g['index1'], g['index2'], g['coeff1'], g['coeff2'], tol=1e-12)
+    x = cpu_be.from_numpy(g['p%d_x' % p].reshape(tuple(g['p%d_shape' % p])))
+    y = plan.matvec(x, 1.0, -float(g['tau'])).numpy().reshape(-1)
+    assert np.abs(y - g['p%d_y' % p]).max() < 1e-13 * max(1.0, np.abs(g['p%d_y' % p]).max())
+    hx = plan.matvec(x, 0.0, 1.0).numpy().reshape(-1)
+    assert np.abs(hx - g['p%d_heff' % p] @ g['p%d_x' % p]).max() < 1e-12
+
+
+def test_observables_vs_reference(golden, cpu_be):
+    from tnalg_b200.MPSClass import MpsOpenBoundaryClass
+    g = golden('percall_j1j2')
+    L, d, chi = int(g['l']), int(g['d']), int(g['chi'])
+    A = MpsOpenBoundaryClass(L, d, chi, operators=[np.real(o) for o in g['op']])
+    for n in range(L):
+        A.mps[n] = g['ob_mps_%d' % n]
+    A.center = 4
+    assert np.abs(A.observe_magnetization(1) - g['ob_mx']).max() < 1e-13
+    assert np.abs(A.observe_magnetization(3) - g['ob_mz']).max() < 1e-13
+    assert np.abs(A.observe_bond_energy(g['index2'], g['coeff2']) - g['ob_eb_full']).max() < 1e-13
+    assert np.abs(A.observe_correlators_from_middle(3, 3) - g['ob_corr_z']).max() < 1e-13
+    assert np.abs(A.observe_correlators_from_middle(1, 1) - g['ob_corr_x']).max() < 1e-13
+    assert abs(A.norm_mps() - float(g['ob_norm'])) < 1e-13
+    assert abs(A.observation_s1((3, 2)) - g['ob_mz'][2, 0]) < 1e-13
+    # centre at either end: same numbers (gauge invariance of the observable pass)
+    for c in (0, L - 1):
+        A.correct_orthogonal_center(c)
+        assert np.abs(A.observe_magnetization(3) - g['ob_mz']).max() < 1e-12
+        assert np.abs(A.observe_bond_energy(g['index2'], g['coeff2']) - g['ob_eb_full']).max() < 1e-12
+
+
+@pytest.mark.parametrize('case', ['e2e_chain12', 'e2e_xxz10', 'e2e_j1j2_4x2'])
+def test_end_to_end_vs_reference(golden, cpu_be, case):
+    """dmrg_finite_size through the product's host code: converged energies / spectrum rel 1e-10, observables 1e-8"""
+    from tnalg_b200.DMRG_anyH import dmrg_finite_size
+    g = golden(case)
+    para = para_from_golden(g)
+    np.random.seed(int(g['seed']))
+    ob, A, info, para = dmrg_finite_size(para)
+    assert abs(ob['e_per_site'][0] - g['e_per_site'][0]) <= 1e-10 * abs(g['e_per_site'][0])
+    for k in ('eb_full', 'eb', 'mx', 'mz', 'corr_x', 'corr_z'):
+        assert np.abs(np.asarray(ob[k]).reshape(-1) - g[k].reshape(-1)).max() < 1e-8, k
+    assert np.abs(A.ent - g['ent']).max() < 1e-8
+    for n in range(para['l'] - 1):
+        ref = g['lm_%d' % n]
+        assert np.abs(A.lm[n] - ref).max() <= 1e-10 * ref.max() + 1e-12, n
+    assert np.array_equal(A.virtual_dim, g['virtual_dim'])
+    assert info['not_converged'] == 0
+    # one batched bond move per local update instead of the reference's per-term chains
+    assert set(ob.keys()) == {'eb_full', 'mx', 'mz', 'e_per_site', 'eb', 'corr_x', 'corr_z'}
+    assert {'convergence', 't_cost'} <= set(info.keys())
+
+
+def test_pr_layout_roundtrip(golden, cpu_be, tmp_path):
+    """`.pr` = pickle of {name: obj}; the MPS object pickles to the reference attribute set with numpy tensors"""
+    from tnalg_b200 import BasicFunctionsSJR as Bf
+    from tnalg_b200.DMRG_anyH import dmrg_finite_size
+    g = golden('e2e_chain12')
+    para = para_from_golden(g, sweep_time=2, dt_ob=2)
+    np.random.seed(0)
+    ob, A, info, para = dmrg_finite_size(para)
+    Bf.save_pr(str(tmp_path), 'x.pr', (ob, A, info, para), ('ob', 'A', 'info', 'para'))
+    data = Bf.load_pr(str(tmp_path / 'x.pr'))
+    assert set(data.keys()) == {'ob', 'A', 'info', 'para'}
+    B = data['A']
+    ref_attrs = set(str(k) for k in g['attrs'])                       # today's reference class (MPSClass.py:53-106)
+    old_attrs = set(str(k) for k in golden('pr_fixtures')['chi16_attrs'])  # the 2018 fixtures hold a subset
+    assert set(B.__dict__.keys()) == ref_attrs and old_attrs <= ref_attrs
+    assert all(isinstance(t, np.ndarray) and t.dtype == np.float64 for t in B.mps)
+    assert [t.shape for t in B.mps] == [(A.virtual_dim[n], 2, A.virtual_dim[n + 1]) for n in range(12)]
+    ob2 = Bf.load_pr(str(tmp_path / 'x.pr'), 'ob')
+    assert np.array_equal(ob2['mz'], ob['mz'])
+    assert Bf.load_pr(str(tmp_path / 'missing.pr')) is False
+    # a revived object keeps working (tensors go back to the device lazily)
+    assert abs(B.norm_mps() - 1.0) < 1e-12
+    assert np.abs(B.observe_magnetization(3) - ob['mz']).max() < 1e-12
+
+
+def test_cache_invalidation_on_external_gauge_change(golden, cpu_be):
+    """re-gauging between updates (what breaks the reference's corr_*) must not leave stale blocks behind"""
+    from tnalg_b200.MPSClass import MpsOpenBoundaryClass
+    g = golden('percall_j1j2')
+    L, d, chi = int(g['l']), int(g['d']), int(g['chi'])
+    A = MpsOpenBoundaryClass(L, d, chi, operators=[np.real(o) for o in g['op']])
+    for n in range(L):
+        A.mps[n] = g['mps_%d' % n]
+    A.center = int(g['center0'])
+    args = (g['index1'], g['index2'], g['coeff1'], g['coeff2'])
+    A.correct_orthogonal_center(4)
+    plan = A.effective_hamiltonian_plan(4, *args, tol=1e-12)
+    x = cpu_be.from_numpy(np.random.RandomState(0).randn(*A.mps[4].shape))
+    e_before = float((x * plan.matvec(x)).sum())
+    A.calculate_entanglement_spectrum()          # SVD re-gauge of every bond, centre returns to 4
+    plan2 = A.effective_hamiltonian_plan(4, *args, tol=1e-12)
+    # H_eff in the new gauge is a different matrix, but <psi|H|psi> of the state itself is gauge invariant
+    psi = A.mps[4]
+    e_state = float((psi * plan2.matvec(psi)).sum()) / float((psi * psi).sum())
+    ref = g['p4_mps_4']
+    assert abs(e_state - float(ref.reshape(-1) @ g['p4_heff'] @ ref.reshape(-1)) / float((ref ** 2).sum())) < 1e-12
+    assert np.isfinite(e_before)
+
+
+def test_term_table_rejects_unsorted_sites():
+    from tnalg_b200.envs import TermTable
+    ops = [np.eye(2)] * 7
+    with pytest.raises(ValueError):
+        TermTable(np.zeros((0, 2)), np.array([[3, 1, 3, 3]]), np.zeros(0), np.ones(1), ops, 1e-12)

@@ -1,0 +1,89 @@
+"""dmrg_finite_size: the sweep driver of the reference (DMRG_anyH.py:18-101) on the CUDA path.
+
+Same signature and return value: dmrg_finite_size(para) -> (ob, A, info, para) with
+ob keys eb_full, mx, mz, e_per_site, eb, corr_x, corr_z and info keys convergence, t_cost.
+Extra (non-reference) info keys: n_sweeps, n_solves, n_matvec, flops_algorithmic, flops_executed.
+"""
+import time
+
+import numpy as np
+
+from . import Parameters as pm
+from .MPSClass import MpsOpenBoundaryClass as Mob
+
+is_debug = False
+
+
+def sweep_order(length, ob_position):
+    """site order of one sweep: right from ob_position+1, back to 0, then up to ob_position-1 (DMRG_anyH.py:47-64)"""
+    return list(range(ob_position + 1, length)) + list(range(length - 2, -1, -1)) + list(range(1, ob_position))
+
+
+def sweep_once(A, para):
+    for n in sweep_order(para['l'], para['ob_position']):
+        A.update_tensor_eigs(n, para['index1'], para['index2'], para['coeff1'], para['coeff2'], para['tau'],
+                             para['is_real'], tol=para['eigs_tol'])
+
+
+def observe(A, para, ob):
+    ob['eb_full'] = A.observe_bond_energy(para['index2'], para['coeff2'])
+    ob['mx'] = A.observe_magnetization(1)
+    ob['mz'] = A.observe_magnetization(3)
+    ob['e_per_site'] = (sum(ob['eb_full']) - para['hx'] * sum(ob['mx']) - para['hz'] * sum(ob['mz'])) / A.length
+    return ob
+
+
+def dmrg_finite_size(para=None, quiet=True):
+    t_start = time.time()
+    info = dict()
+    if para is None:
+        para = pm.generate_parameters_dmrg()
+    say = (lambda *a: None) if quiet else print
+    A = Mob(length=para['l'], d=para['d'], chi=para['chi'], way='qr', ini_way='r', operators=para['op'], debug=is_debug,
+            is_parallel=para['isParallel'], par_pool=None, is_save_op=para['is_save_op'], eig_way=para['eigWay'],
+            is_env_parallel_lmr=para['isParallelEnvLMR'])
+    A.correct_orthogonal_center(para['ob_position'])
+    e0_per_site = 0
+    info['convergence'] = 1
+    info['n_sweeps'] = 0
+    ob = dict()
+    for t in range(0, para['sweep_time']):
+        if_ob = ((t + 1) % para['dt_ob'] == 0) or t == (para['sweep_time'] - 1)
+        sweep_once(A, para)
+        info['n_sweeps'] = t + 1
+        if if_ob:
+            observe(A, para, ob)
+            info['convergence'] = abs(ob['e_per_site'] - e0_per_site)
+            if info['convergence'] < para['break_tol']:
+                say('Converged at the %d-th sweep with error = %g of energy per site.' % (t + 1, info['convergence']))
+                break
+            say('Convergence error of energy per site = %g' % info['convergence'])
+            e0_per_site = ob['e_per_site']
+        if t == para['sweep_time'] - 1 and info['convergence'] > para['break_tol']:
+            say('Not converged with error = %g of eb per bond' % info['convergence'])
+    ob['eb'] = get_bond_energies(ob['eb_full'], para['positions_h2'], para['index2'])
+    A.calculate_entanglement_spectrum()
+    A.calculate_entanglement_entropy()
+    ob['corr_x'] = A.observe_correlators_from_middle(1, 1)
+    ob['corr_z'] = A.observe_correlators_from_middle(3, 3)
+    info['t_cost'] = time.time() - t_start
+    info.update({k: A.stats[k] for k in ('n_solves', 'n_matvec', 'flops_algorithmic', 'flops_executed', 'not_converged')})
+    say('Simulation finished in %g seconds' % info['t_cost'])
+    A.clean_to_save()
+    return ob, A, info, para
+
+
+def get_bond_energies(eb_full, positions, index2):
+    """sum the per-term energies onto their bond (DMRG_anyH.py:250-258)"""
+    positions = np.asarray(positions)
+    eb = np.zeros((positions.shape[0], 1))
+    for i in range(0, eb_full.size):
+        p = (index2[i, 0] == positions[:, 0]) * (index2[i, 1] == positions[:, 1])
+        eb[np.nonzero(p)] += eb_full[i]
+    return eb
+
+
+def sort_positions(pos):
+    """rows sorted lexicographically (used by Parameters.from_index2_to_positions_h2 in the reference)"""
+    pos = np.asarray(pos)
+    return pos[np.lexsort((pos[:, 1], pos[:, 0]))]

@@ -1,0 +1,408 @@
+"""Drop-in replacement of the reference's MPSClass.MpsOpenBoundaryClass for the finite-size DMRG path.
+
+Same constructor signature, attribute set, method names and pickled layout as MPSClass.py:26-1098 of the reference
+(root-level generation); the numpy/scipy arithmetic underneath is replaced by the CUDA library through
+tnalg_b200.ops (C ABI in include/tnalg_b200.h).  The MPS tensors live on the GPU for the whole run and are turned
+into numpy arrays by clean_to_save() / pickling, so `.pr` files written through BasicFunctionsSJR.save_pr keep the
+reference layout.
+
+Deliberate differences:
+  * effective operators are kept as summed complementary blocks per bond (tnalg_b200.envs) instead of one matrix
+    per term per bond; `effect_s`, `effect_ss`, `pos_effect_*`, `effective_id`, `opt_env` exist for layout
+    compatibility and stay empty;
+  * observables are always computed from the actual tensors, so corr_* after calculate_entanglement_spectrum() are
+    the correct values, not the reference's stale-cache values;
+  * the eigensolver is a device-resident thick-restart Lanczos with ARPACK's convergence criterion;
+  * is_parallel / is_env_parallel_lmr / par_pool are accepted and ignored (the GPU batches terms itself).
+"""
+import numpy as np
+
+from . import ops as _ops
+from .envs import EnvCache, TermTable, expect_products
+from .HamiltonianModule import spin_operators
+
+VERSION = '2018-06-3'  # MPSClass.py:15, kept so that pickles look alike
+
+
+class _TensorList(list):
+    """list of site tensors that converts assigned numpy arrays to device tensors and tells the owner which site
+    changed (so that cached environments are invalidated)."""
+
+    def __init__(self, owner, items):
+        super().__init__(items)
+        self._owner = owner
+
+    def __setitem__(self, n, value):
+        owner = self._owner
+        if not hasattr(value, 'data_ptr'):
+            value = owner._be.from_numpy(np.real(value))
+        super().__setitem__(n, value)
+        owner._tensor_changed(n)
+
+    def __reduce__(self):
+        return (list, (list(self),))
+
+
+class MpsBasic:
+    def __init__(self):
+        self.version = VERSION
+        self.operators = list()
+
+    def append_operators(self, op_new):
+        if type(op_new) is np.ndarray:
+            self.operators.append(op_new)
+        else:
+            for n in range(0, len(op_new)):
+                self.operators.append(op_new[n])
+
+
+_STATE_KEYS = ('version', 'operators', 'spin', 'phys_dim', 'decomp_way', 'length', 'orthogonality', 'center', 'lm',
+               'ent', 'mps', 'virtual_dim', '_is_save_op', 'effect_s', 'pos_effect_s', 'effect_ss', 'pos_effect_ss',
+               'effective_id', 'opt_env', '_is_parallel', 'pool', '_debug', 'eig_way', '_is_env_parallel_lmr')
+
+
+class MpsOpenBoundaryClass(MpsBasic):
+    """Open-boundary MPS with the reference's interface (MPSClass.py:53-55):
+    MpsOpenBoundaryClass(length, d, chi, spin='half', way='qr', ini_way='r', operators=None, debug=False,
+                         is_parallel=False, is_save_op=False, eig_way=0, par_pool=None, is_env_parallel_lmr=True)"""
+
+    def __init__(self, length, d, chi, spin='half', way='qr', ini_way='r', operators=None, debug=False,
+                 is_parallel=False, is_save_op=False, eig_way=0, par_pool=None, is_env_parallel_lmr=True):
+        MpsBasic.__init__(self)
+        self.spin = spin
+        self.phys_dim = d
+        self.decomp_way = way
+        self.length = length
+        self.orthogonality = np.zeros((length, 1))
+        self.center = -1
+        self.lm = [np.zeros(0) for _ in range(length - 1)]
+        self.ent = np.zeros((self.length - 1, 1))
+        self._be = _ops.backend()
+        if ini_way == 'r':
+            # same np.random.randn draw order as random_open_mps (TensorBasicModule.py:181-186)
+            host = [None] * length
+            host[0] = np.random.randn(1, d, chi)
+            host[length - 1] = np.random.randn(chi, d, 1)
+            for n in range(1, length - 1):
+                host[n] = np.random.randn(chi, d, chi)
+        elif ini_way == '1':
+            host = [np.ones((1, d, chi))] + [np.ones((chi, d, chi)) for _ in range(length - 2)] + [np.ones((chi, d, 1))]
+        else:
+            raise ValueError("ini_way must be 'r' or '1'")
+        self.mps = _TensorList(self, [self._be.from_numpy(t) for t in host])
+        self.virtual_dim = np.ones((length + 1,)).astype(int) * chi
+        self.virtual_dim[0] = 1
+        self.virtual_dim[-1] = 1
+        if operators is None:
+            op_half = spin_operators(spin)
+            self.operators = [op_half['id'], op_half['sx'], op_half['sy'], op_half['sz'], op_half['su'], op_half['sd']]
+        else:
+            self.operators = operators
+        self._is_save_op = is_save_op
+        self.effect_s = {'none': np.zeros(0)}
+        self.pos_effect_s = np.zeros((0, 3)).astype(int)
+        self.effect_ss = {'none': np.zeros(0)}
+        self.pos_effect_ss = np.zeros((0, 5)).astype(int)
+        self.effective_id = {'none': np.zeros(0)}
+        self.opt_env = dict()
+        self._is_parallel = is_parallel
+        self.pool = None
+        self._debug = debug
+        self.eig_way = eig_way
+        self._is_env_parallel_lmr = is_env_parallel_lmr
+        self._init_runtime()
+
+    # ---- runtime (non-pickled) state ----
+    def _init_runtime(self):
+        self._env = None
+        self._env_key = None
+        self.stats = {'n_solves': 0, 'n_matvec': 0, 'flops_algorithmic': 0.0, 'flops_executed': 0.0,
+                      't_solve': 0.0, 'not_converged': 0}
+        self.lanczos_ncv = 20           # ARPACK's default ncv for k=1 (scipy eigsh)
+        self.lanczos_max_restarts = 2000
+        self.timing = False             # when True, update_tensor_eigs records solver time with CUDA events
+        self._events = []
+
+    def _ensure_device(self):
+        if not hasattr(self, '_be') or self._be is None:
+            self._be = _ops.backend()
+        if not hasattr(self, '_env'):
+            self._init_runtime()
+        if not isinstance(self.mps, _TensorList):
+            self.mps = _TensorList(self, [t if hasattr(t, 'data_ptr') else self._be.from_numpy(np.real(t))
+                                          for t in self.mps])
+            self._env = None
+
+    def _tensor_changed(self, n):
+        env = getattr(self, '_env', None)
+        if env is not None:
+            env.invalidate_site(n)
+
+    def __getstate__(self):
+        state = {}
+        for k in _STATE_KEYS:
+            v = getattr(self, k)
+            if k == 'mps':
+                v = [self._be.to_numpy(t) if hasattr(t, 'data_ptr') else np.asarray(t) for t in v]
+            state[k] = v
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+
+    # ---- gauge moves (a7: orthogonalize_mps / correct_orthogonal_center, MPSClass.py:143-198) ----
+    def _decompose(self, n, left2right):
+        """left2right/right2left_decompose_tensor (TensorBasicModule.py:314-384): returns (Q tensor, R, dim, lm) with
+        T = Q R (left2right, R is (k,b)) or T = R^T-absorbed form (right2left)."""
+        be = self._be
+        T = self.mps[n]
+        a, d, b = T.shape
+        mat = T.reshape(a * d, b) if left2right else T.reshape(a, d * b).t().contiguous()
+        k = min(mat.shape)
+        if self.decomp_way == 1 or self.decomp_way == 'svd':
+            U, S, Vt = be.svd(mat)
+            R = be.scale_diag_rows(S, Vt)
+            lm = be.to_numpy(S)
+            Q = U
+        else:
+            Q, R = be.qr(mat)
+            lm = np.zeros(0)
+        if left2right:
+            Qt = Q.contiguous().reshape(a, d, k)
+        else:
+            Qt = Q.t().contiguous().reshape(k, d, b)
+        return Qt, R, k, lm
+
+    def orthogonalize_mps(self, l0, l1):
+        self._ensure_device()
+        be = self._be
+        if l0 < l1:
+            for n in range(l0, l1):
+                Q, R, dim, lm = self._decompose(n, True)
+                self.virtual_dim[n + 1] = dim
+                if lm.size > 0 and self.center > -1:
+                    self.lm[n] = lm.copy()
+                self.mps[n] = Q
+                # absorb_matrix2tensor(mps[n+1], R^T, 0): new[k,s,b] = sum_j R[k,j] T[j,s,b]
+                self.mps[n + 1] = be.mode_product(self.mps[n + 1], R.t().contiguous(), 0)
+            self.orthogonality[l0:l1] = -1
+            self.orthogonality[l1] = 0
+        elif l0 > l1:
+            for n in range(l0, l1, -1):
+                Q, R, dim, lm = self._decompose(n, False)
+                self.virtual_dim[n] = dim
+                if lm.size > 0 and self.center > -1:
+                    self.lm[n - 1] = lm.copy()
+                self.mps[n] = Q
+                # absorb_matrix2tensor(mps[n-1], R^T, 2): new[a,s,k] = sum_j T[a,s,j] R[k,j]
+                self.mps[n - 1] = be.mode_product(self.mps[n - 1], R.t().contiguous(), 2)
+            self.orthogonality[l0:l1:-1] = 1
+            self.orthogonality[l1] = 0
+
+    def central_orthogonalization(self, lc, l0=0, l1=-1):
+        if l1 == -1:
+            l1 = self.length - 1
+        self.orthogonalize_mps(l0, lc)
+        self.orthogonalize_mps(l1, lc)
+        self.center = lc
+
+    def correct_orthogonal_center(self, p=-1):
+        if p < -0.5 and self.center < -0.5:
+            p = self.check_orthogonal_center(if_print=False)
+        elif p < -0.5:
+            p = self.center
+        if self.center < -0.5:
+            self.central_orthogonalization(p)
+        elif self.center != p:
+            self.orthogonalize_mps(self.center, p)
+        self.center = p
+
+    def check_orthogonal_center(self, expected_center=-2, if_print=True):
+        """recommend a centre from self.orthogonality (MPSClass.py:989-1024), no tensor is touched"""
+        if self.center > -0.5:
+            return self.center
+        left = np.nonzero(self.orthogonality.reshape(-1) == -1)[0]
+        return int(left[-1]) + 1 if left.size else 0
+
+    # ---- a1/a2/a8: the local update (update_tensor_eigs, MPSClass.py:778-809) ----
+    def _environments(self, index1, index2, coeff1, coeff2, tol):
+        key = (id(index1), id(index2), id(coeff1), id(coeff2), float(tol), len(self.operators))
+        if self._env is None or self._env_key != key:
+            terms = TermTable(index1, index2, coeff1, coeff2, self.operators, tol)
+            if terms.length > self.length:
+                raise ValueError('coupling terms reference site %d but the MPS has %d sites' % (terms.length - 1, self.length))
+            self._env = EnvCache(self._be, terms, self.length)
+            self._env_key = key
+            self._env_refs = (index1, index2, coeff1, coeff2)  # keep the ids alive
+        return self._env
+
+    def _dist(self):
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and getattr(self, 'shard_terms', True):
+                return dist
+        except Exception:
+            pass
+        return None
+
+    def effective_hamiltonian_plan(self, p, index1, index2, coeff1, coeff2, tol=1e-12, rank=0, world=1):
+        """tn_effh_plan for site p (the opt_env groups of all_environments_optimized, MPSClass.py:633-682)."""
+        self._ensure_device()
+        env = self._environments(index1, index2, coeff1, coeff2, tol)
+        return env.plan(p, self.mps, rank=rank, world=world)
+
+    def update_tensor_eigs(self, p, index1, index2, coeff1, coeff2, tau, is_real, tol=1e-16):
+        import torch
+        self._ensure_device()
+        if self.center < -0.5:
+            raise RuntimeError('CenterError: central-orthogonalize MPS before updating the tensor')
+        self.correct_orthogonal_center(p)
+        dist = self._dist()
+        rank, world = (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
+        plan = self.effective_hamiltonian_plan(p, index1, index2, coeff1, coeff2, tol=tol, rank=rank, world=world)
+        shape = tuple(self.mps[p].shape)
+        allreduce = None
+        if dist is not None:
+            dev = self._be.device
+
+            def allreduce(buf, count, user, stream):
+                try:
+                    t = _alias_tensor(buf, count, dev)
+                    dist.all_reduce(t)
+                    return 0
+                except Exception:  # pragma: no cover
+                    return 1
+        if self.timing:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        lam, vec, n_mv, resid, ok = self._be.lanczos(plan, tau, self.mps[p].reshape(-1), tol, ncv=self.lanczos_ncv,
+                                                     max_restarts=self.lanczos_max_restarts, allreduce=allreduce)
+        if self.timing:
+            e1.record()
+            self._events.append((e0, e1))
+        if dist is not None:
+            dist.broadcast(vec, src=0)  # keep the replicas bit-identical
+        self.stats['n_solves'] += 1
+        self.stats['n_matvec'] += n_mv
+        self.stats['flops_algorithmic'] += n_mv * plan.flops_algorithmic
+        self.stats['flops_executed'] += n_mv * plan.flops_executed
+        self.stats['not_converged'] += 0 if ok else 1
+        self.last_eig = {'lambda': lam, 'residual': resid, 'n_matvec': n_mv, 'converged': ok}
+        plan.destroy()
+        self.mps[p] = vec.reshape(shape)
+        if self.eig_way == 1:
+            self.opt_env = dict()
+
+    def solver_time_ms(self):
+        """sum of the CUDA-event durations recorded by update_tensor_eigs while self.timing was True"""
+        import torch
+        torch.cuda.synchronize()
+        t = sum(e0.elapsed_time(e1) for e0, e1 in self._events)
+        self._events = []
+        return t
+
+    # ---- a11: entanglement (MPSClass.py:812-839) ----
+    def calculate_entanglement_spectrum(self, if_fast=True):
+        self._ensure_device()
+        _way, _center = self.decomp_way, self.center
+        self.decomp_way = 'svd'
+        if if_fast and _center > -0.5:
+            p0, p1 = self.length - 1, 0
+            for n in range(0, self.length - 1):
+                if self.lm[n].size == 0:
+                    p0, p1 = min(p0, n), max(p1, n)
+            self.correct_orthogonal_center(p0)
+            self.correct_orthogonal_center(p1 + 1)
+            self.correct_orthogonal_center(_center)
+        else:
+            self.correct_orthogonal_center(0)
+            self.correct_orthogonal_center(self.length - 1)
+            if _center > 0:
+                self.correct_orthogonal_center(_center)
+        self.decomp_way = _way
+
+    def calculate_entanglement_entropy(self):
+        from .TensorBasicModule import entanglement_entropy
+        for i in range(0, self.length - 1):
+            self.ent[i] = -1 if self.lm[i].size == 0 else entanglement_entropy(self.lm[i])
+
+    # ---- a10: observables (MPSClass.py:857-952) ----
+    def _expect(self, terms):
+        self._ensure_device()
+        if self.center < -0.5:
+            raise RuntimeError('observables need a centre-orthogonal MPS; call correct_orthogonal_center first')
+        ops = [np.real(np.asarray(o)).astype(float) if np.abs(np.imag(np.asarray(o))).max() == 0 else None
+               for o in self.operators]
+        out = []
+        for i in range(0, len(terms), 1024):
+            out.append(expect_products(self._be, self.mps, self.center, ops, terms[i:i + 1024]))
+        return np.concatenate(out) if out else np.zeros(0)
+
+    def observation_s1(self, inputs):
+        sn, position = inputs
+        return self._expect([((position, sn),)])[0]
+
+    def observation_s1_s2(self, inputs):
+        ssn, positions = inputs
+        pair = sorted(zip([int(positions[0]), int(positions[1])], [int(ssn[0]), int(ssn[1])]))
+        return self._expect([tuple(pair)])[0]
+
+    def observe_magnetization(self, sn):
+        return self._expect([((i, sn),) for i in range(self.length)]).reshape(-1, 1)
+
+    def observe_bond_energy(self, index2, coeff2):
+        index2 = np.asarray(index2, dtype=int)
+        terms = [tuple(sorted(((int(r[0]), int(r[2])), (int(r[1]), int(r[3]))))) for r in index2]
+        vals = self._expect(terms)
+        return (np.asarray(coeff2, dtype=float).reshape(-1) * vals).reshape(-1, 1)
+
+    def observe_correlators_from_middle(self, op1, op2, ob_len=None):
+        if ob_len is None:
+            ob_len = self.length
+        pairs = []
+        pos_mid = round(self.length / 2)
+        pos1, pos2, n_control = pos_mid, pos_mid + 1, 0
+        while pos1 > -0.1 and pos2 < self.length and ob_len > -0.1:
+            pairs.append(((pos1, op1), (pos2, op2)))
+            if n_control % 2 == 0:
+                pos1 -= 1
+            else:
+                pos2 += 1
+            n_control += 1
+            ob_len -= 1
+        return self._expect(pairs)
+
+    def norm_mps(self):
+        self._ensure_device()
+        if self.center < -0.5:
+            raise RuntimeError('norm_mps needs a centre-orthogonal MPS')
+        return self._be.norm(self.mps[self.center])
+
+    # ---- housekeeping ----
+    def report_yourself(self):
+        print('center: ' + str(self.center))
+        print('orthogonality:' + str(self.orthogonality.T))
+        print('virtual bond dimensions: ' + str(self.virtual_dim))
+
+    def clean_to_save(self):
+        """drop caches and bring the tensors to the host as numpy arrays (MPSClass.py:1090-1098)"""
+        self.mps = [self._be.to_numpy(t) if hasattr(t, 'data_ptr') else np.asarray(t) for t in self.mps]
+        self.effect_s = {'none': np.zeros(0)}
+        self.effect_ss = {'none': np.zeros(0)}
+        self.effective_id = {'none': np.zeros(0)}
+        self.pos_effect_s = np.zeros((0, 3)).astype(int)
+        self.pos_effect_ss = np.zeros((0, 5)).astype(int)
+        self.pool = None
+        self._env = None
+        self._env_key = None
+
+
+def _alias_tensor(ptr, count, device):
+    """torch view of `count` float64 values at device address `ptr` (used by the all-reduce callback)."""
+    import torch
+
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {'shape': (int(count),), 'typestr': '<f8', 'data': (int(ptr), False), 'version': 2}
+    return torch.as_tensor(h, device=device)

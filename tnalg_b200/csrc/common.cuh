@@ -1,0 +1,127 @@
+// Shared host/device helpers for libtnalg_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "tnalg_b200.h"
+
+namespace tn {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+int sm_count();
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// carve aligned pieces out of a caller-provided workspace
+struct Carver {
+  char* base;
+  size_t size, used;
+  Carver(void* p, size_t n) : base(static_cast<char*>(p)), size(n), used(0) {}
+  template <class T>
+  T* take(size_t count) {
+    size_t bytes = align_up(count * sizeof(T));
+    if (used + bytes > size) return nullptr;
+    T* r = reinterpret_cast<T*>(base + used);
+    used += bytes;
+    return r;
+  }
+};
+
+#define TN_CUDA(x)                                                                                      \
+  do {                                                                                                  \
+    cudaError_t e_ = (x);                                                                               \
+    if (e_ != cudaSuccess) {                                                                            \
+      tn::set_error("%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__);          \
+      return TN_ERR_CUDA;                                                                               \
+    }                                                                                                   \
+  } while (0)
+
+#define TN_REQUIRE(cond, ...)         \
+  do {                                \
+    if (!(cond)) {                    \
+      tn::set_error(__VA_ARGS__);     \
+      return TN_ERR_INVALID;          \
+    }                                 \
+  } while (0)
+
+#define TN_LAUNCHED()                                                                                   \
+  do {                                                                                                  \
+    ++tn::g_launches;                                                                                   \
+    cudaError_t e_ = cudaGetLastError();                                                                \
+    if (e_ != cudaSuccess) {                                                                            \
+      tn::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__);    \
+      return TN_ERR_CUDA;                                                                               \
+    }                                                                                                   \
+  } while (0)
+
+#define TN_CHECK(x)          \
+  do {                       \
+    int s_ = (x);            \
+    if (s_ != TN_OK) return s_; \
+  } while (0)
+
+// ---- device-side descriptors of the chain GEMM (built by the host wrappers in chain_gemm.cu) ----
+constexpr int kMaxD = TN_MAX_PHYS_DIM;
+
+struct LinkDev {
+  const double* A;
+  const double* B;
+  double op[kMaxD * kMaxD];
+  int has_op;
+  int a_dyn;  // 1: A = params.dyn_in (psi of this matvec call)
+  int b_dyn;  // 1: B = params.dyn_in
+  int pad;
+};
+
+struct ProblemDev {
+  double* C;
+  double alpha;
+  int link_begin, link_count;
+  int accumulate;
+  int c_dyn;             // 1: C = params.dyn_out and alpha is multiplied by params.dyn_alpha
+  long long work_begin;  // prefix sum of tiles*iters (stream-K) over the problems of the launch
+  long long tile_begin;  // prefix sum of tiles
+};
+
+struct GemmParams {
+  int M, N, K, d;
+  int lda, ldb, ldc;
+  int n_problems;
+  int tiles_m, tiles_n;
+  int ipl;  // k-iterations per link = ceil(K / BK)
+  int split;  // 1: stream-K over [0,total_work) with atomics; 0: whole tiles, direct stores
+  const ProblemDev* problems;
+  const LinkDev* links;
+  long long total_work, work_per_cta, total_tiles;
+  const double* dyn_in;
+  double* dyn_out;
+  double dyn_alpha;
+};
+
+// internal launch entry shared by the plan / env-update / public wrappers
+struct GemmLaunch {
+  int mode, M, N, K, d, lda, ldb, ldc;
+  int n_problems, n_links;
+  int deterministic;
+};
+// fills work_begin/tile_begin of `problems` (host copies), chooses tile config + split policy.
+struct GemmSchedule {
+  int config;  // 0 = 128x128 tiles, 1 = 64x64 tiles
+  int aligned16;
+  int split;
+  int grid;
+  int tiles_m, tiles_n, ipl;
+  long long total_work, work_per_cta, total_tiles;
+};
+int gemm_plan_schedule(const GemmLaunch& L, ProblemDev* problems_host, const LinkDev* links_host, const double* dyn_in,
+                       const double* dyn_out, GemmSchedule* S);
+int gemm_launch(const GemmLaunch& L, const GemmSchedule& S, const ProblemDev* problems_dev, const LinkDev* links_dev,
+                const double* dyn_in, double* dyn_out, double dyn_alpha, cudaStream_t stream);
+
+}  // namespace tn

@@ -1,0 +1,82 @@
+// Small dense-math routines shared by device kernels and CPU unit tests (tests/test_host_math.py builds this
+// header with g++).  No CUDA-specific constructs besides the TN_HD qualifier.
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define TN_HD __host__ __device__
+#else
+#define TN_HD
+#endif
+
+namespace tn {
+
+constexpr int kMaxNcv = 64;
+
+TN_HD inline double tn_sign(double a, double b) { return b >= 0.0 ? fabs(a) : -fabs(a); }
+
+// Symmetric tridiagonal eigenproblem by implicit QL with Wilkinson shifts.
+//   d[0..n)  diagonal in, eigenvalues out (unsorted);  e[i] couples i and i+1 (e[n-1] ignored, destroyed);
+//   z (n x n, row-major, leading dimension ldz) must hold the identity on entry; column k is the eigenvector of d[k].
+// Returns 0 on success, 1 when an eigenvalue needed more than 60 iterations.
+TN_HD inline int tridiag_ql(int n, double* d, double* e, double* z, int ldz) {
+  if (n <= 0) return 0;
+  e[n - 1] = 0.0;
+  for (int l = 0; l < n; ++l) {
+    int iter = 0;
+    int m;
+    do {
+      for (m = l; m < n - 1; ++m) {
+        const double dd = fabs(d[m]) + fabs(d[m + 1]);
+        if (fabs(e[m]) <= 2.3e-16 * dd) break;
+      }
+      if (m != l) {
+        if (iter++ == 60) return 1;
+        double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+        double r = hypot(g, 1.0);
+        g = d[m] - d[l] + e[l] / (g + tn_sign(r, g));
+        double s = 1.0, c = 1.0, p = 0.0;
+        int i;
+        for (i = m - 1; i >= l; --i) {
+          double f = s * e[i];
+          const double b = c * e[i];
+          r = hypot(f, g);
+          e[i + 1] = r;
+          if (r == 0.0) {
+            d[i + 1] -= p;
+            e[m] = 0.0;
+            break;
+          }
+          s = f / r;
+          c = g / r;
+          g = d[i + 1] - p;
+          r = (d[i] - g) * s + 2.0 * c * b;
+          p = s * r;
+          d[i + 1] = g + p;
+          g = c * r - b;
+          for (int k = 0; k < n; ++k) {
+            f = z[k * ldz + i + 1];
+            z[k * ldz + i + 1] = s * z[k * ldz + i] + c * f;
+            z[k * ldz + i] = c * z[k * ldz + i] - s * f;
+          }
+        }
+        if (r == 0.0 && i >= l) continue;
+        d[l] -= p;
+        e[l] = g;
+        e[m] = 0.0;
+      }
+    } while (m != l);
+  }
+  return 0;
+}
+
+// One-sided Jacobi rotation for the column pair with squared norms (alpha, beta) and inner product gamma:
+// returns (c, s) such that  p' = c p - s q,  q' = s p + c q  are orthogonal.
+TN_HD inline void jacobi_rotation(double alpha, double beta, double gamma, double* c, double* s) {
+  const double zeta = (beta - alpha) / (2.0 * gamma);
+  const double t = tn_sign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+  *c = 1.0 / sqrt(1.0 + t * t);
+  *s = *c * t;
+}
+
+}  // namespace tn

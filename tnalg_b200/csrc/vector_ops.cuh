@@ -1,0 +1,28 @@
+// Memory-bound helper kernels shared by the plan, the Lanczos driver and the SVD (HBM roofline class).
+#pragma once
+#include "common.cuh"
+
+namespace tn {
+
+struct SiteOp {
+  double m[kMaxD * kMaxD];
+};
+
+// out[a,s,b] = c_id * x[a,s,b] + c_op * sum_s' op[s,s'] x[a,s',b]     (x is (a,d,b) C-order)
+int launch_site_op_axpby(double* out, const double* x, long long a, int d, long long b, double c_id, double c_op,
+                         const SiteOp& op, cudaStream_t stream);
+
+// deterministic dot products: result[i] = sum_e V[i*ldv + e] * w[e], i < nvec.  partial: nvec * dot_chunks(n) doubles,
+// counter: one unsigned zero-initialised once (the kernel resets it).  Optional fused bookkeeping is done by callers
+// in a follow-up single-thread kernel.
+int dot_chunks(long long n);
+int launch_multidot(const double* V, long long ldv, int nvec, const double* w, long long n, double* result, double* partial,
+                    unsigned* counter, cudaStream_t stream);
+// w[e] -= sum_i h[i] * V[i*ldv + e]
+int launch_multi_axpy(double* w, const double* V, long long ldv, int nvec, const double* h, long long n, cudaStream_t stream);
+// y[e] = sum_i u[i] * V[i*ldv + e]
+int launch_combine(double* y, const double* V, long long ldv, int nvec, const double* u, long long n, cudaStream_t stream);
+// x[e] *= *scale (device scalar)
+int launch_scale_dev(double* x, const double* scale, long long n, cudaStream_t stream);
+
+}  // namespace tn

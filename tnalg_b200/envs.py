@@ -1,0 +1,316 @@
+"""Term algebra and environment bookkeeping for the one-site effective Hamiltonian.
+
+Replaces the reference's operator cache (a2-a4: all_environments_optimized / classify_and_update_env /
+get_effective_operators_* / update_all_effective_id, MPSClass.py:203-325, 474-530, 633-733), which keeps one
+(chi,chi) matrix per coupling term per bond and re-runs L-1 identity transfers on every local update.
+
+Here every bond keeps *summed complementary operators* (SURVEY.md section 7.6):
+  left block of bond p  (depends on sites < p):   HL[p]            sum of every term wholly left of the bond
+                                                  OL[p][(i, s)]    op s of site i < p that still has a partner >= p
+  right block of bond p (depends on sites >= p):  HR[p], OR[p][(j, s)]
+and a bond move is ONE batched tn_env_update call.  The groups handed to the matvec are exactly the reference's
+opt_env groups ('1_0_0', '0_0_1', '0_s_0', '1_s_0', '0_s_1', '1_0_1'), so results agree term by term; only the
+floating-point summation order differs.  Validity is tracked per site tensor, so a gauge change made by any method
+(including calculate_entanglement_spectrum, whose stale cache makes the reference's corr_* wrong, SURVEY.md
+section 4) invalidates exactly the blocks that depend on it.
+"""
+import numpy as np
+
+
+class TermTable:
+    """Filtered coupling terms.  Mirrors the filters of all_environments_optimized (MPSClass.py:643-652):
+    one-body terms need |c| > tol and ||op|| > tol, two-body terms |c| > tol; tol is the eigensolver tolerance."""
+
+    def __init__(self, index1, index2, coeff1, coeff2, operators, tol):
+        self.ops = [np.real(np.asarray(o)).astype(float) if np.abs(np.imag(np.asarray(o))).max() == 0 else None
+                    for o in operators]
+        index1 = np.asarray(index1, dtype=int).reshape(-1, 2)
+        index2 = np.asarray(index2, dtype=int).reshape(-1, 4)
+        coeff1 = np.asarray(coeff1, dtype=float).reshape(-1)
+        coeff2 = np.asarray(coeff2, dtype=float).reshape(-1)
+        self.one = []  # (site, op, c)
+        for n in range(index1.shape[0]):
+            site, sn, c = int(index1[n, 0]), int(index1[n, 1]), float(coeff1[n])
+            if abs(c) > tol and np.linalg.norm(np.asarray(operators[sn])) > tol:
+                self.one.append((site, sn, c))
+        self.two = []  # (i, j, op_i, op_j, c) with i < j
+        for n in range(index2.shape[0]):
+            i, j, si, sj = (int(x) for x in index2[n])
+            c = float(coeff2[n])
+            if abs(c) > tol:
+                if not i < j:
+                    raise ValueError('two-body term %d has site1 >= site2 (%d, %d); the reference path is only '
+                                     'correct for site1 < site2 (MPSClass.py:652,717-728)' % (n, i, j))
+                self.two.append((i, j, si, sj, c))
+        for _, sn, _ in self.one:
+            self._real_op(sn)
+        for _, _, si, sj, _ in self.two:
+            self._real_op(si), self._real_op(sj)
+        self.length = 1 + max([t[0] for t in self.one] + [t[1] for t in self.two] + [0])
+
+    def _real_op(self, sn):
+        if self.ops[sn] is None:
+            raise ValueError('operator %d is complex; the is_real path only supports real site operators' % sn)
+        return self.ops[sn]
+
+    def site_field(self, p, d):
+        """sum of the one-body operators acting on site p (the '0_s_0' group), or None"""
+        m = None
+        for site, sn, c in self.one:
+            if site == p:
+                m = c * self.ops[sn] if m is None else m + c * self.ops[sn]
+        return m
+
+    def open_left(self, p):
+        """(i, s) pairs with i < p that have a partner j >= p  (operators alive on the left block of bond p)"""
+        return sorted({(i, si) for i, j, si, sj, c in self.two if i < p <= j})
+
+    def open_right(self, p):
+        """(j, s) pairs with j >= p that have a partner i < p"""
+        return sorted({(j, sj) for i, j, si, sj, c in self.two if i < p <= j})
+
+    def any_left_of(self, p):
+        """is there any term wholly inside sites < p"""
+        return any(site < p for site, _, _ in self.one) or any(j < p for _, j, _, _, _ in self.two)
+
+    def any_right_of(self, p):
+        """is there any term wholly inside sites >= p"""
+        return any(site >= p for site, _, _ in self.one) or any(i >= p for i, _, _, _, _ in self.two)
+
+    def closing_left(self, p):
+        """terms (i, p): {s_p: [(c, (i, s_i)), ...]} -- the '1_s_0' groups at site p"""
+        g = {}
+        for i, j, si, sj, c in self.two:
+            if j == p:
+                g.setdefault(sj, []).append((c, (i, si)))
+        return g
+
+    def closing_right(self, p):
+        """terms (p, j): {s_p: [(c, (j, s_j)), ...]} -- the '0_s_1' groups at site p"""
+        g = {}
+        for i, j, si, sj, c in self.two:
+            if i == p:
+                g.setdefault(si, []).append((c, (j, sj)))
+        return g
+
+    def crossing(self, p):
+        """terms (i, j) with i < p < j: [(c, (i, s_i), (j, s_j))] -- the '1_0_1' list at site p"""
+        return [(c, (i, si), (j, sj)) for i, j, si, sj, c in self.two if i < p < j]
+
+    def counts(self, p):
+        """(K_L, K_R, n_x) of SURVEY.md section 8d for site p"""
+        kl = len(self.closing_left(p)) + (1 if self.any_left_of(p) else 0)
+        kr = len(self.closing_right(p)) + (1 if self.any_right_of(p + 1) else 0)
+        return kl, kr, len(self.crossing(p))
+
+
+class EnvCache:
+    """Left/right blocks of every bond for one TermTable, kept on the device."""
+
+    def __init__(self, be, terms, length):
+        self.be, self.terms, self.L = be, terms, length
+        self.left = [None] * (length + 1)   # bond p: {'H': tensor|None, 'O': {(i,s): tensor}}
+        self.right = [None] * (length + 1)
+        self.left[0] = {'H': None, 'O': {}}
+        self.right[length] = {'H': None, 'O': {}}
+        self.lv = 0        # left blocks of bonds 0..lv are valid
+        self.rv = length   # right blocks of bonds rv..L are valid
+        self.n_bond_moves = 0
+
+    def invalidate_site(self, n):
+        """tensor n changed: left blocks of bonds > n and right blocks of bonds <= n are stale"""
+        if n < self.lv:
+            for p in range(n + 1, self.lv + 1):
+                self.left[p] = None
+            self.lv = n
+        if n + 1 > self.rv:
+            for p in range(self.rv, n + 1):
+                self.right[p] = None
+            self.rv = n + 1
+
+    def invalidate_all(self):
+        for n in range(self.L):
+            self.invalidate_site(n)
+
+    # ---- bond moves ----
+    def _lincomb(self, block, pairs):
+        xs = [block['O'][key] for _, key in pairs]
+        cs = [c for c, _ in pairs]
+        if len(xs) == 1 and cs[0] == 1.0:
+            return xs[0]
+        return self.be.lincomb(xs, cs)
+
+    def _advance_left(self, p, T):
+        """left block of bond p+1 from bond p and the (left-orthonormal) tensor of site p"""
+        t, cur = self.terms, self.left[p]
+        outputs, keys = [], []
+        links = []
+        if cur['H'] is not None:
+            links.append((cur['H'], None))
+        for s, pairs in sorted(t.closing_left(p).items()):
+            links.append((self._lincomb(cur, pairs), t.ops[s]))
+        field = t.site_field(p, T.shape[1])
+        if field is not None:
+            links.append((None, field))
+        if links:
+            outputs.append(links)
+            keys.append('H')
+        for key in t.open_left(p + 1):
+            i, s = key
+            outputs.append([(None, t.ops[s])] if i == p else [(cur['O'][key], None)])
+            keys.append(key)
+        new = {'H': None, 'O': {}}
+        if outputs:
+            res = self.be.env_update(0, T, outputs)
+            for key, mat in zip(keys, res):
+                if key == 'H':
+                    new['H'] = mat
+                else:
+                    new['O'][key] = mat
+        self.left[p + 1] = new
+        self.n_bond_moves += 1
+
+    def _advance_right(self, p, T):
+        """right block of bond p from bond p+1 and the (right-orthonormal) tensor of site p"""
+        t, cur = self.terms, self.right[p + 1]
+        outputs, keys = [], []
+        links = []
+        if cur['H'] is not None:
+            links.append((cur['H'], None))
+        for s, pairs in sorted(t.closing_right(p).items()):
+            links.append((self._lincomb(cur, pairs), t.ops[s]))
+        field = t.site_field(p, T.shape[1])
+        if field is not None:
+            links.append((None, field))
+        if links:
+            outputs.append(links)
+            keys.append('H')
+        for key in t.open_right(p):
+            j, s = key
+            outputs.append([(None, t.ops[s])] if j == p else [(cur['O'][key], None)])
+            keys.append(key)
+        new = {'H': None, 'O': {}}
+        if outputs:
+            res = self.be.env_update(1, T, outputs)
+            for key, mat in zip(keys, res):
+                if key == 'H':
+                    new['H'] = mat
+                else:
+                    new['O'][key] = mat
+        self.right[p] = new
+        self.n_bond_moves += 1
+
+    def ensure(self, p, mps):
+        """make the left block of bond p and the right block of bond p+1 valid (centre at p)"""
+        while self.lv < p:
+            self._advance_left(self.lv, mps[self.lv])
+            self.lv += 1
+        while self.rv > p + 1:
+            self._advance_right(self.rv - 1, mps[self.rv - 1])
+            self.rv -= 1
+
+    # ---- the opt_env groups of site p (MPSClass.py:684-733) ----
+    def groups(self, p, d):
+        t, lb, rb = self.terms, self.left[p], self.right[p + 1]
+        g = {'HL': lb['H'], 'HR': rb['H'], 'M': t.site_field(p, d), 'LS': [], 'ls_ops': [], 'RS': [], 'rs_ops': [],
+             'XL': [], 'XR': [], 'x_coeff': []}
+        for s, pairs in sorted(t.closing_left(p).items()):
+            g['LS'].append(self._lincomb(lb, pairs))
+            g['ls_ops'].append(t.ops[s])
+        for s, pairs in sorted(t.closing_right(p).items()):
+            g['RS'].append(self._lincomb(rb, pairs))
+            g['rs_ops'].append(t.ops[s])
+        for c, lk, rk in t.crossing(p):
+            g['XL'].append(lb['O'][lk])
+            g['XR'].append(rb['O'][rk])
+            g['x_coeff'].append(c)
+        return g
+
+    def plan(self, p, mps, rank=0, world=1):
+        self.ensure(p, mps)
+        a, d, b = mps[p].shape
+        g = self.groups(p, d)
+        return self.be.effh_plan((a, d, b), g['HL'], g['HR'], g['M'], g['LS'], g['ls_ops'], g['RS'], g['rs_ops'],
+                                 g['XL'], g['XR'], g['x_coeff'], rank=rank, world=world)
+
+
+def expect_products(be, mps, center, ops, terms):
+    """<prod_k op[s_k](site_k)> for every term in `terms` (list of tuples of (site, op_id), sites strictly increasing
+    inside a term) on a centre-orthogonal MPS (sites < center left-, sites > center right-orthonormal).
+    a10: observation_s1 / observation_s1_s2 (MPSClass.py:857-909) restated as one left-to-right pass:
+    operator-carrying environments are shared by all terms with the same leading (site, op), the far sides are the
+    identity or a 'density' chain rho from the centre, and every bond is one batched tn_env_update call.
+    Returns a float numpy array of len(terms)."""
+    L = len(mps)
+    if not terms:
+        return np.zeros(0)
+    terms = [tuple((int(s), int(o)) for s, o in term) for term in terms]
+    for term in terms:
+        sites = [s for s, _ in term]
+        if sites != sorted(set(sites)) or not (0 <= sites[0] and sites[-1] < L):
+            raise ValueError('observable sites must be strictly increasing and inside the chain: %r' % (term,))
+    first = min(term[0][0] for term in terms)
+    last = max(term[-1][0] for term in terms)
+    # right density chain: rhoR[q] closes bond q when every site >= q carries no operator and q <= center
+    rhoR = {}
+    lo = min(term[-1][0] for term in terms) + 1  # smallest closing bond
+    if lo <= center:
+        cur = None
+        for q in range(center, lo - 1, -1):
+            cur = be.env_update(1, mps[q], [[(cur, None)]])[0]
+            rhoR[q] = cur
+    slots, slot_of = [], {}
+    # active[(prefix term tuple)] = environment at the current bond carrying those operators; () is the plain density
+    active = {}
+    need_rho_left = any(term[0][0] > center for term in terms)
+    for q in range(min(first, center) if need_rho_left else first, last + 1):
+        outputs, keys = [], []
+        # which prefixes must exist on bond q+1
+        want = set()
+        for term in terms:
+            sites = [s for s, _ in term]
+            if sites[0] > q:
+                if q >= center and sites[0] > center:
+                    want.add(())      # density still travelling towards the first operator
+                continue
+            if sites[-1] < q:
+                continue
+            k = sum(1 for s in sites if s <= q)  # operators absorbed up to and including site q
+            want.add(term[:k])
+        for pre in sorted(want):
+            if pre and pre[-1][0] == q:      # absorbs an operator on this site
+                parent = pre[:-1]
+                op = ops[pre[-1][1]]
+            else:
+                parent, op = pre, None
+            if parent == ():
+                env = active.get(()) if q > center else None   # identity unless a density has left the centre
+                if q > center and env is None:
+                    raise RuntimeError('internal: missing density chain at site %d' % q)
+            else:
+                env = active[parent]
+            if env is None and op is None:
+                # identity through a left-orthonormal site stays the identity; only q == center starts the density
+                if q < center:
+                    continue
+            outputs.append([(env, op)])
+            keys.append(pre)
+        new_active = {}
+        if outputs:
+            res = be.env_update(0, mps[q], outputs)
+            new_active = dict(zip(keys, res))
+        active = new_active
+        # close the terms that end on this site
+        for n, term in enumerate(terms):
+            if term[-1][0] == q:
+                env = active[term]
+                if q >= center:
+                    slot = be.trace(env)
+                else:
+                    slot = be.dot(env, rhoR[q + 1])
+                slot_of[n] = len(slots)
+                slots.append(slot)
+                if len(slots) >= 2048:
+                    raise RuntimeError('too many observables in one call')
+    vals = be.scalars_to_host(slots)
+    return np.array([vals[slot_of[n]] for n in range(len(terms))])
