@@ -1,0 +1,110 @@
+"""End-to-end parity of the CUDA path (through the drop-in API) with the reference goldens -- run on the B200 box."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def para_from_golden(g, **kw):
+    from tnalg_b200 import Parameters as Pm
+    para = dict(Pm.common_parameters_dmrg())
+    ops = [np.real(o) if np.abs(np.imag(o)).max() == 0 else o for o in g['op']]
+    para.update(lattice='arbitrary', spin='half', op=ops, index1=g['index1'], coeff1=g['coeff1'], index2=g['index2'],
+                coeff2=g['coeff2'], chi=int(g['chi']), tau=float(g['tau']), eigs_tol=float(g['eigs_tol']),
+                break_tol=float(g['break_tol']), hx=float(g['hx']), hz=float(g['hz']))
+    para.update(kw)
+    return Pm.make_consistent_parameter_dmrg(para)
+
+
+@pytest.mark.parametrize('p', [0, 2, 4, 5, 8])
+def test_matvec_on_reference_snapshot(golden, p):
+    """identical MPS -> the CUDA environments + matvec reproduce the reference handle output (a1..a5)"""
+    from tnalg_b200 import ops
+    from tnalg_b200.MPSClass import MpsOpenBoundaryClass
+    be = ops.backend()
+    g = golden('percall_j1j2')
+    L, d, chi = int(g['l']), int(g['d']), int(g['chi'])
+    A = MpsOpenBoundaryClass(L, d, chi, operators=[np.real(o) for o in g['op']], is_save_op=True, eig_way=1)
+    for n in range(L):
+        A.mps[n] = g['p%d_mps_%d' % (p, n)]
+    A.center = p
+    plan = A.effective_hamiltonian_plan(p, g['index1'], g['index2'], g['coeff1'], g['coeff2'], tol=1e-12)
+    x = be.from_numpy(g['p%d_x' % p].reshape(tuple(g['p%d_shape' % p])))
+    y = be.to_numpy(plan.matvec(x, 1.0, -float(g['tau']))).reshape(-1)
+    assert np.abs(y - g['p%d_y' % p]).max() < 1e-13 * max(1.0, np.abs(g['p%d_y' % p]).max())
+    hx = be.to_numpy(plan.matvec(x, 0.0, 1.0)).reshape(-1)
+    ref = g['p%d_heff' % p] @ g['p%d_x' % p]
+    assert np.abs(hx - ref).max() < 1e-13 * np.abs(ref).max()
+
+
+def test_observables_on_reference_snapshot(golden):
+    from tnalg_b200.MPSClass import MpsOpenBoundaryClass
+    g = golden('percall_j1j2')
+    L, d, chi = int(g['l']), int(g['d']), int(g['chi'])
+    A = MpsOpenBoundaryClass(L, d, chi, operators=[np.real(o) for o in g['op']])
+    for n in range(L):
+        A.mps[n] = g['ob_mps_%d' % n]
+    A.center = 4
+    assert np.abs(A.observe_magnetization(1) - g['ob_mx']).max() < 1e-12
+    assert np.abs(A.observe_magnetization(3) - g['ob_mz']).max() < 1e-12
+    assert np.abs(A.observe_bond_energy(g['index2'], g['coeff2']) - g['ob_eb_full']).max() < 1e-12
+    assert np.abs(A.observe_correlators_from_middle(3, 3) - g['ob_corr_z']).max() < 1e-12
+    assert np.abs(A.observe_correlators_from_middle(1, 1) - g['ob_corr_x']).max() < 1e-12
+    for c in (0, L - 1):
+        A.correct_orthogonal_center(c)
+        assert np.abs(A.observe_magnetization(3) - g['ob_mz']).max() < 1e-11
+
+
+@pytest.mark.parametrize('case', ['e2e_chain12', 'e2e_xxz10', 'e2e_j1j2_4x2'])
+def test_end_to_end_vs_reference(golden, case):
+    """converged, tight-tolerance runs: sweep energies and truncated spectrum rel 1e-10, observables abs 1e-8"""
+    from tnalg_b200.DMRG_anyH import dmrg_finite_size
+    g = golden(case)
+    para = para_from_golden(g)
+    np.random.seed(int(g['seed']))
+    ob, A, info, para = dmrg_finite_size(para)
+    assert abs(ob['e_per_site'][0] - g['e_per_site'][0]) <= 1e-10 * abs(g['e_per_site'][0])
+    for k in ('eb_full', 'eb', 'mx', 'mz', 'corr_x', 'corr_z'):
+        assert np.abs(np.asarray(ob[k]).reshape(-1) - g[k].reshape(-1)).max() < 1e-8, k
+    assert np.abs(A.ent - g['ent']).max() < 1e-8
+    for n in range(para['l'] - 1):
+        ref = g['lm_%d' % n]
+        assert np.abs(A.lm[n] - ref).max() <= 1e-10 * ref.max() + 1e-12, n
+    assert np.array_equal(A.virtual_dim, g['virtual_dim'])
+    assert info['not_converged'] == 0
+    assert all(isinstance(t, np.ndarray) for t in A.mps)
+
+
+def test_size_independent_properties_chi64():
+    """larger than the oracle can check quickly: properties the domain offers.
+    (1) the matvec is symmetric <x|H y> = <y|H x>; (2) the Lanczos energy is variational and non-increasing along
+    the sweep; (3) the state stays normalised; (4) observables computed with the centre at both ends agree."""
+    from tnalg_b200 import Parameters as Pm, ops
+    from tnalg_b200.DMRG_anyH import sweep_once
+    from tnalg_b200.MPSClass import MpsOpenBoundaryClass
+    be = ops.backend()
+    para = Pm.generate_parameters_dmrg('square')
+    para.update(square_width=4, square_height=4, chi=64, op=para['op'][:6])
+    para = Pm.make_consistent_parameter_dmrg(para)
+    np.random.seed(4)
+    A = MpsOpenBoundaryClass(para['l'], para['d'], para['chi'], operators=para['op'], is_save_op=True, eig_way=1)
+    A.correct_orthogonal_center(0)
+    sweep_once(A, para)
+    A.correct_orthogonal_center(7)
+    plan = A.effective_hamiltonian_plan(7, para['index1'], para['index2'], para['coeff1'], para['coeff2'], tol=1e-5)
+    rng = np.random.RandomState(0)
+    x, y = be.from_numpy(rng.randn(*A.mps[7].shape)), be.from_numpy(rng.randn(*A.mps[7].shape))
+    xhy = float((x * plan.matvec(y)).sum())
+    yhx = float((y * plan.matvec(x)).sum())
+    assert abs(xhy - yhx) < 1e-11 * max(abs(xhy), 1.0)
+    energies = []
+    for _ in range(3):
+        sweep_once(A, para)
+        eb = A.observe_bond_energy(para['index2'], para['coeff2'])
+        energies.append(float(eb.sum()))
+        assert abs(A.norm_mps() - 1) < 1e-12
+    assert energies[1] <= energies[0] + 1e-9 and energies[2] <= energies[1] + 1e-9
+    mz0 = A.observe_magnetization(3)
+    A.correct_orthogonal_center(para['l'] - 1)
+    assert np.abs(A.observe_magnetization(3) - mz0).max() < 1e-10
+    assert abs(float(A.observe_bond_energy(para['index2'], para['coeff2']).sum()) - energies[-1]) < 1e-9

@@ -1,0 +1,280 @@
+"""Parity of every C-ABI entry point against the numpy oracle on identical seeded inputs (run on the B200 box)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import dmrg_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def be():
+    from tnalg_b200 import ops
+    return ops.backend()
+
+
+def rel_err(x, ref):
+    return np.abs(np.asarray(x) - ref).max() / max(np.abs(ref).max(), 1e-300)
+
+
+def chain_gemm(be, mode, M, N, K, d, problems, deterministic):
+    """problems: list of (alpha, accumulate, C0 (M,N) numpy, [ (A, B, op or None) ]) -> list of results"""
+    import torch
+    from tnalg_b200 import _lib as L
+    n_links = sum(len(p[3]) for p in problems)
+    probs = (L.TnProblem * len(problems))()
+    links = (L.TnLink * n_links)()
+    keep, outs, li = [], [], 0
+    for q, (alpha, acc, C0, lk) in enumerate(problems):
+        Cd = be.from_numpy(C0)
+        outs.append(Cd)
+        probs[q].C, probs[q].alpha, probs[q].link_begin, probs[q].link_count, probs[q].accumulate = Cd.data_ptr(), alpha, li, len(lk), acc
+        for A, B, op in lk:
+            Ad, Bd = be.from_numpy(A), be.from_numpy(B)
+            keep += [Ad, Bd]
+            links[li].A, links[li].B, links[li].has_op = Ad.data_ptr(), Bd.data_ptr(), 0 if op is None else 1
+            if op is not None:
+                for i, v in enumerate(np.asarray(op).reshape(-1)):
+                    links[li].op[i] = v
+            li += 1
+    lda = M if mode == 2 else K
+    ldb = K if mode == 1 else N
+    ws = torch.empty(be.lib.tn_chain_gemm_workspace_bytes(len(problems), n_links) + 256, dtype=torch.uint8, device=be.device)
+    L.check(be.lib.tn_chain_gemm(mode, M, N, K, d, lda, ldb, N, probs, len(problems), links, n_links, deterministic,
+                                 C.c_void_p(ws.data_ptr()), ws.numel(), be.stream()))
+    torch.cuda.synchronize()
+    return [be.to_numpy(o) for o in outs]
+
+
+def ref_link(mode, d, A, B, op):
+    if mode == 0:      # A (M,K) . opcol(B (K, d*Ny))
+        if op is not None:
+            K, N = B.shape
+            B = np.einsum('st,kty->ksy', op, B.reshape(K, d, N // d)).reshape(K, N)
+        return A @ B
+    if mode == 1:      # oprow(A (Mx*d, K)) . B(N,K)^T
+        if op is not None:
+            M, K = A.shape
+            A = np.einsum('st,xtk->xsk', op, A.reshape(M // d, d, K)).reshape(M, K)
+        return A @ B.T
+    return A.T @ B     # A (K,M), B (K,N)
+
+
+SHAPES = [(1, 2, 1), (2, 4, 2), (5, 6, 3), (16, 16, 16), (33, 18, 7), (64, 64, 64), (100, 36, 50), (130, 258, 70),
+          (256, 256, 96), (257, 129, 33)]
+
+
+@pytest.mark.parametrize('mode', [0, 1, 2])
+@pytest.mark.parametrize('d', [1, 2, 3])
+@pytest.mark.parametrize('deterministic', [1, 0])
+def test_chain_gemm_shapes(be, mode, d, deterministic):
+    rng = np.random.RandomState(100 * mode + 10 * d + deterministic)
+    if mode == 2 and d > 1:
+        pytest.skip('TN has no operator')
+    for (M, N, K) in SHAPES:
+        if mode == 0:
+            N = N * d
+        if mode == 1:
+            M = M * d
+        shapeA = (K, M) if mode == 2 else (M, K)
+        shapeB = (N, K) if mode == 1 else (K, N)
+        problems, refs = [], []
+        for q, n_links in enumerate([3, 1]):
+            lk = []
+            ref = np.zeros((M, N))
+            for l in range(n_links):
+                A, B = rng.randn(*shapeA), rng.randn(*shapeB)
+                op = rng.randn(d, d) if (d > 1 and l != 1) else None
+                lk.append((A, B, op))
+                ref += ref_link(mode, d, A, B, op)
+            alpha, acc = (0.7, 1) if q == 0 else (-1.3, 0)
+            C0 = rng.randn(M, N)
+            refs.append(alpha * ref + (C0 if acc else 0))
+            problems.append((alpha, acc, C0, lk))
+        outs = chain_gemm(be, mode, M, N, K, d, problems, deterministic)
+        for o, r in zip(outs, refs):
+            assert rel_err(o, r) < 1e-13, (mode, d, M, N, K)
+
+
+def test_chain_gemm_large_split_and_deterministic(be):
+    """chi=512-like sizes: the 128x128 configuration, stream-K split vs whole tiles, run-to-run determinism"""
+    rng = np.random.RandomState(7)
+    M, N, K, d = 512, 512, 512, 2
+    lk = [(rng.randn(M, K), rng.randn(N, K), rng.randn(d, d) if l % 2 else None) for l in range(4)]
+    ref = sum(ref_link(1, d, *x) for x in lk)
+    C0 = np.zeros((M, N))
+    o_split = chain_gemm(be, 1, M, N, K, d, [(1.0, 0, C0, lk)], 0)[0]
+    o_det1 = chain_gemm(be, 1, M, N, K, d, [(1.0, 0, C0, lk)], 1)[0]
+    o_det2 = chain_gemm(be, 1, M, N, K, d, [(1.0, 0, C0, lk)], 1)[0]
+    assert rel_err(o_split, ref) < 1e-13 and rel_err(o_det1, ref) < 1e-13
+    assert np.array_equal(o_det1, o_det2)
+
+
+@pytest.mark.parametrize('shape', [(1, 2, 2), (2, 2, 4), (4, 2, 8), (16, 2, 16), (7, 3, 9), (64, 2, 32), (96, 2, 96), (130, 2, 128)])
+def test_env_update_vs_oracle(be, shape):
+    rng = np.random.RandomState(sum(shape))
+    a, d, b = shape
+    T = rng.randn(a, d, b)
+    ops = [rng.randn(d, d) for _ in range(3)]
+    for direction, e_dim, fn in ((0, a, orc.transfer_l2r), (1, b, orc.transfer_r2l)):
+        Es = [rng.randn(e_dim, e_dim) for _ in range(3)]
+        outputs_np = [
+            [(Es[0], None), (Es[1], ops[0]), (None, ops[1])],   # an HL-like chain
+            [(Es[2], None)],                                    # plain transfer
+            [(None, ops[2])],                                   # new operator, identity environment
+            [(None, None)],                                     # identity transfer (density chain)
+            [(Es[1], ops[2])],
+        ]
+        outputs = [[(None if E is None else be.from_numpy(E), op) for E, op in links] for links in outputs_np]
+        res = be.env_update(direction, be.from_numpy(T), outputs)
+        for r, links in zip(res, outputs_np):
+            ref = sum(fn(T, op, E) for E, op in links)
+            assert rel_err(be.to_numpy(r), ref) < 1e-13, (shape, direction)
+
+
+def random_groups(rng, a, d, b, n_ls, n_rs, n_x, with_h=True, with_m=True):
+    sym = lambda n: (lambda g: (g + g.T) / 2)(rng.randn(n, n))  # noqa: E731
+    return {'HL': sym(a) if with_h else None, 'HR': sym(b) if with_h else None, 'M': rng.randn(d, d) if with_m else None,
+            'LS': [rng.randn(a, a) for _ in range(n_ls)], 'ls_ops': [rng.randn(d, d) for _ in range(n_ls)],
+            'RS': [rng.randn(b, b) for _ in range(n_rs)], 'rs_ops': [rng.randn(d, d) for _ in range(n_rs)],
+            'XL': [rng.randn(a, a) for _ in range(n_x)], 'XR': [rng.randn(b, b) for _ in range(n_x)],
+            'x_coeff': list(rng.randn(n_x))}
+
+
+def gpu_plan(be, shape, g, rank=0, world=1):
+    t = lambda x: None if x is None else be.from_numpy(x)  # noqa: E731
+    return be.effh_plan(shape, t(g['HL']), t(g['HR']), g['M'], [t(x) for x in g['LS']], g['ls_ops'], [t(x) for x in g['RS']],
+                        g['rs_ops'], [t(x) for x in g['XL']], [t(x) for x in g['XR']], g['x_coeff'], rank=rank, world=world)
+
+
+@pytest.mark.parametrize('shape,counts', [((1, 2, 2), (0, 3, 0)), ((2, 2, 1), (3, 0, 0)), ((4, 2, 8), (3, 3, 2)), ((16, 2, 16), (3, 3, 0)),
+                                          ((9, 3, 27), (2, 3, 4)), ((64, 2, 64), (3, 3, 9)), ((128, 2, 128), (3, 3, 5)),
+                                          ((256, 2, 256), (3, 3, 2)), ((100, 2, 60), (1, 2, 3))])
+def test_matvec_vs_oracle(be, shape, counts):
+    from tests.cpu_backend import CpuPlan
+    rng = np.random.RandomState(sum(shape) + sum(counts))
+    a, d, b = shape
+    g = random_groups(rng, a, d, b, *counts)
+    ref_plan = CpuPlan(shape, g)
+    plan = gpu_plan(be, shape, g)
+    x = rng.randn(a, d, b)
+    hx = ref_plan.apply(x.reshape(-1))
+    y = be.to_numpy(plan.matvec(be.from_numpy(x), 0.0, 1.0)).reshape(-1)
+    assert rel_err(y, hx) < 1e-13, shape
+    tau = 1e-4
+    y = be.to_numpy(plan.matvec(be.from_numpy(x), 1.0, -tau)).reshape(-1)
+    assert np.abs(y - (x.reshape(-1) - tau * hx)).max() < 1e-15 * max(1.0, np.abs(hx).max())
+    assert plan.flops_algorithmic == ref_plan.flops_algorithmic
+    # sharded plans sum to the full operator (multi-GPU term sharding)
+    parts = [be.to_numpy(gpu_plan(be, shape, g, rank=r, world=3).matvec(be.from_numpy(x), 1.0, -tau)).reshape(-1) for r in range(3)]
+    assert np.abs(sum(parts) - y).max() < 1e-14 * max(1.0, np.abs(y).max())
+
+
+def test_matvec_without_any_block(be):
+    """a site with only an on-site field (no environment blocks at all) still works"""
+    rng = np.random.RandomState(3)
+    g = random_groups(rng, 4, 2, 4, 0, 0, 0, with_h=False)
+    x = rng.randn(4, 2, 4)
+    y = be.to_numpy(gpu_plan(be, (4, 2, 4), g).matvec(be.from_numpy(x), 0.0, 1.0))
+    assert rel_err(y, np.einsum('st,atb->asb', g['M'], x)) < 1e-14
+
+
+@pytest.mark.parametrize('shape,counts', [((1, 2, 2), (0, 3, 0)), ((2, 2, 4), (3, 3, 1)), ((8, 2, 8), (3, 3, 2)), ((24, 2, 24), (3, 3, 4)),
+                                          ((64, 2, 64), (3, 3, 3))])
+@pytest.mark.parametrize('tol', [1e-5, 1e-12])
+def test_lanczos_vs_dense_eigh(be, shape, counts, tol):
+    """dominant eigenpair of 1 - tau*H_eff: eigenvalue, residual and (for tight tol) the eigenvector itself"""
+    from tests.cpu_backend import CpuPlan
+    rng = np.random.RandomState(11 + sum(shape))
+    a, d, b = shape
+    g = random_groups(rng, a, d, b, *counts)
+    # make every piece symmetric so that H_eff is symmetric, as it is in DMRG
+    for k in ('LS', 'RS', 'XL', 'XR'):
+        g[k] = [(m + m.T) / 2 for m in g[k]]
+    for k in ('ls_ops', 'rs_ops'):
+        g[k] = [(m + m.T) / 2 for m in g[k]]
+    g['M'] = (g['M'] + g['M'].T) / 2
+    ref_plan = CpuPlan(shape, g)
+    n = a * d * b
+    H = np.stack([ref_plan.apply(e) for e in np.eye(n)], axis=1)
+    assert np.abs(H - H.T).max() < 1e-12
+    tau = 1e-4
+    w, v = np.linalg.eigh(np.eye(n) - tau * H)
+    k = int(np.argmax(np.abs(w)))
+    plan = gpu_plan(be, shape, g)
+    v0 = rng.randn(n)
+    lam, vec, n_mv, resid, ok = be.lanczos(plan, tau, be.from_numpy(v0), tol, ncv=20, max_restarts=500)
+    vec = be.to_numpy(vec)
+    assert ok
+    assert abs(np.linalg.norm(vec) - 1) < 1e-13
+    r = (np.eye(n) - tau * H) @ vec - lam * vec
+    assert np.linalg.norm(r) <= 2 * tol * abs(lam) + 1e-14
+    if tol < 1e-10:
+        assert abs(lam - w[k]) < 1e-13
+        assert min(np.linalg.norm(vec - v[:, k]), np.linalg.norm(vec + v[:, k])) < 1e-6
+    assert n_mv >= min(n, 2)
+
+
+@pytest.mark.parametrize('shape', [(1, 1), (2, 1), (1, 5), (4, 4), (8, 3), (3, 8), (37, 21), (64, 64), (130, 64), (64, 130), (256, 128)])
+def test_svd_jacobi_vs_lapack(be, shape):
+    rng = np.random.RandomState(shape[0] * 7 + shape[1])
+    m, n = shape
+    # graded singular values: Schmidt spectra span many decades
+    k = min(m, n)
+    A = np.linalg.qr(rng.randn(m, k))[0] @ np.diag(np.logspace(0, -12, k)) @ np.linalg.qr(rng.randn(n, k))[0].T
+    U, S, Vt = [be.to_numpy(x) for x in be.svd(be.from_numpy(A))]
+    s_ref = np.linalg.svd(A, compute_uv=False)
+    assert np.abs(S - s_ref).max() <= 1e-10 * s_ref.max()          # north_star tolerance
+    assert np.abs(S / s_ref - 1).max() < 1e-6                      # Jacobi: small values to high relative accuracy
+    assert np.abs(U.T @ U - np.eye(k)).max() < 1e-12
+    assert np.abs(Vt @ Vt.T - np.eye(k)).max() < 1e-12
+    assert np.abs((U * S) @ Vt - A).max() < 1e-13
+    if k >= 4:
+        kk = k // 2
+        U2, S2, Vt2 = [be.to_numpy(x) for x in be.svd(be.from_numpy(A), k_keep=kk)]
+        assert U2.shape == (m, kk) and Vt2.shape == (kk, n)
+        assert np.abs(S2 - s_ref[:kk]).max() <= 1e-10 * s_ref.max()
+        assert np.abs((U2 * S2) @ Vt2 - (U[:, :kk] * S[:kk]) @ Vt[:kk]).max() < 1e-12
+
+
+def test_svd_matches_cusolver_baseline(be):
+    """cuSOLVER (torch.linalg.svd) is kept only as a checked baseline (north_star)"""
+    import torch
+    rng = np.random.RandomState(5)
+    A = be.from_numpy(rng.randn(192, 96))
+    U, S, Vt = be.svd(A)
+    S_ref = torch.linalg.svdvals(A)
+    assert float((S - S_ref).abs().max()) <= 1e-12 * float(S_ref.max())
+
+
+def test_two_site_svd_truncate_vs_oracle(be):
+    """a12: two-site (a*d x d*b) SVD truncated to chi (library/MPSClass.py:1676-1686)"""
+    from tnalg_b200 import TensorBasicModule as T
+    rng = np.random.RandomState(9)
+    theta = rng.randn(12, 2, 2, 10)
+    U, lm, Vh = T.svd_truncate_two_site(theta, 8)
+    U0, lm0, Vh0 = orc.svd_truncate_two_site(theta, 8)
+    assert U.shape == (12, 2, 8) and Vh.shape == (8, 2, 10)
+    assert np.abs(lm - lm0).max() <= 1e-10 * lm0.max()
+    # subspaces agree up to sign
+    assert np.abs(np.abs(np.einsum('asb,asc->bc', U, U0)) - np.eye(8)).max() < 1e-9
+    assert np.abs(np.einsum('ayb,b,bxc->ayxc', U, lm, Vh) - np.einsum('ayb,b,bxc->ayxc', U0, lm0, Vh0)).max() < 1e-10
+
+
+def test_small_ops(be):
+    rng = np.random.RandomState(1)
+    xs = [rng.randn(50, 50) for _ in range(20)]
+    cs = rng.randn(20)
+    out = be.to_numpy(be.lincomb([be.from_numpy(x) for x in xs], cs))
+    assert rel_err(out, sum(c * x for c, x in zip(cs, xs))) < 1e-14
+    T, op = rng.randn(9, 3, 11), rng.randn(3, 3)
+    assert rel_err(be.to_numpy(be.site_op(be.from_numpy(T), op)), np.einsum('st,atb->asb', op, T)) < 1e-14
+    x, y = rng.randn(100003), rng.randn(100003)
+    E = rng.randn(77, 77)
+    vals = be.scalars_to_host([be.dot(be.from_numpy(x), be.from_numpy(y)), be.trace(be.from_numpy(E))])
+    assert abs(vals[0] - x @ y) < 1e-10 and abs(vals[1] - np.trace(E)) < 1e-12
+    for bond, mat in ((0, rng.randn(9, 5)), (2, rng.randn(11, 4)), (1, rng.randn(3, 3))):
+        got = be.to_numpy(be.mode_product(be.from_numpy(T), be.from_numpy(mat), bond))
+        assert rel_err(got, orc.mode_product(T, mat, bond)) < 1e-13, bond
