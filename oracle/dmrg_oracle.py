@@ -363,22 +363,33 @@ class OracleMps:
     def apply_handle(self, psi, env, shape, tau):
         """psi -> psi - tau * H_eff psi (update_tensor_eigs_f_handle_optimized, MPSClass.py:755-776)."""
         t = np.asarray(psi).reshape(shape)
+        a, d, b = shape
         out = t.copy()
+
+        def left(mat, x):   # E . x on bond 0 (absorb_matrix2tensor(x, E.T, 0))
+            return (mat @ x.reshape(a, d * b)).reshape(a, d, b)
+
+        def right(mat, x):  # x . E^T on bond 2
+            return (x.reshape(a * d, b) @ mat.T).reshape(a, d, b)
+
+        def mid(op, x):     # op on bond 1
+            return np.einsum('st,atb->asb', op, x)
+
         for key, val in env.items():
             x = key.split('_')
             if key == '1_0_1':
                 for c, vl, vr in val:
-                    out -= tau * c * np.einsum('ax,xsy,by->asb', vl, t, vr)
+                    out -= tau * c * right(vr, left(vl, t))
             elif x[0] == '1' and x[1] == '0':
-                out -= tau * np.einsum('ax,xsb->asb', val, t)
+                out -= tau * left(val, t)
             elif x[2] == '1' and x[1] == '0':
-                out -= tau * np.einsum('asy,by->asb', t, val)
+                out -= tau * right(val, t)
             elif x[0] == '0' and x[2] == '0':
-                out -= tau * np.einsum('st,atb->asb', val, t)
+                out -= tau * mid(val, t)
             elif x[0] == '1':
-                out -= tau * np.einsum('ax,st,xtb->asb', val, self.operators[int(x[1])], t)
+                out -= tau * left(val, mid(self.operators[int(x[1])], t))
             else:
-                out -= tau * np.einsum('by,st,aty->asb', val, self.operators[int(x[1])], t)
+                out -= tau * right(val, mid(self.operators[int(x[1])], t))
         self.n_matvec += 1
         return out.reshape(-1)
 

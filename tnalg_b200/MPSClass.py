@@ -129,9 +129,32 @@ class MpsOpenBoundaryClass(MpsBasic):
         if not hasattr(self, '_env'):
             self._init_runtime()
         if not isinstance(self.mps, _TensorList):
-            self.mps = _TensorList(self, [t if hasattr(t, 'data_ptr') else self._be.from_numpy(np.real(t))
+            self.mps = _TensorList(self, [t.to(self._be.device) if hasattr(t, 'data_ptr') else self._be.from_numpy(np.real(t))
                                           for t in self.mps])
             self._env = None
+
+    def load_tensors(self, tensors, center, virtual_dim=None):
+        """replace the site tensors by `tensors` (numpy arrays or torch tensors, e.g. pinned host memory or the `mps`
+        list of a revived `.pr` pickle), copy them to the device and declare `center` the orthogonality centre."""
+        be = self._be = _ops.backend()
+        if not hasattr(self, '_env'):
+            self._init_runtime()
+        dev = []
+        for t in tensors:
+            if hasattr(t, 'data_ptr'):
+                dev.append(t.to(be.device, non_blocking=True))
+            else:
+                dev.append(be.from_numpy(np.real(t)))
+        if len(dev) != self.length:
+            raise ValueError('expected %d site tensors, got %d' % (self.length, len(dev)))
+        self.mps = _TensorList(self, dev)
+        self.virtual_dim = np.array([dev[0].shape[0]] + [t.shape[2] for t in dev]) if virtual_dim is None else virtual_dim
+        self.center = center
+        self.orthogonality = np.zeros((self.length, 1))
+        self.orthogonality[:center] = -1
+        self.orthogonality[center + 1:] = 1
+        self._env = None
+        self._env_key = None
 
     def _tensor_changed(self, n):
         env = getattr(self, '_env', None)
