@@ -28,23 +28,24 @@ constexpr int BK = 16;
 constexpr int PAD = 4;
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c[0]), "+d"(c[1])
-               : "d"(a), "d"(b));
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c[0]), "+d"(c[1])
+      : "d"(a), "d"(b));
 }
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+// E doubles per copy: 2 -> 16-byte cp.async.cg, 1 -> 8-byte cp.async.ca.  src_bytes < size zero-fills the rest.
+template <int E>
+__device__ __forceinline__ void cp_async(void* smem, const void* gmem, int src_bytes) {
   unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+  if (E == 2)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
-  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
 template <int BM_, int BN_, int WM_, int WN_, int STAGES_>
@@ -64,31 +65,41 @@ struct SmemLayout {
   static constexpr int B_COLS = (MODE == TN_NT) ? BK : Cfg::BN;
   static constexpr int A_PITCH = A_COLS + PAD, B_PITCH = B_COLS + PAD;
   static constexpr int A_ELEMS = A_ROWS * A_PITCH, B_ELEMS = B_ROWS * B_PITCH;
-  static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS + 16;  // + 9 operator entries, 1 flag (padded to 16)
-  static constexpr size_t BYTES = size_t(STAGE_ELEMS) * Cfg::STAGES * sizeof(double);
+  static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
+  static constexpr int OP_ELEMS = 4 * 16;  // ring of 4 link operators (9 entries + flag, padded to 16)
+  static constexpr size_t BYTES = (size_t(STAGE_ELEMS) * Cfg::STAGES + OP_ELEMS) * sizeof(double);
 };
 
-// Copy a ROWS x COLS tile (COLS even) into shared memory.  row_ptr(r) gives the global address of element
-// (r, 0) or nullptr when the row is out of range; col_limit is the number of valid columns starting at col 0.
-template <int ROWS, int COLS, int PITCH, int THREADS, bool A16, class RowPtr>
-__device__ __forceinline__ void load_tile(double* s, RowPtr row_ptr, int col_limit, int tid, const double* dummy) {
-  if (A16) {
-    constexpr int CPR = COLS / 2;
+// Tile copies.  Every thread owns one column group and PASSES rows, so all addressing is a per-thread constant plus a
+// multiple of the row stride: no branches, out-of-range pieces become zero-byte (zero-filling) copies.
+//   "MK": tile rows = M (or N) index, tile columns = K (contiguous in memory)
+template <int ROWS, int PITCH, int THREADS, int E>
+__device__ __forceinline__ void load_mk(double* s, const double* g, long long ld, int rows_valid, int kvalid, int tid,
+                                        const double* dummy) {
+  constexpr int CPR = BK / E, RSTEP = THREADS / CPR, PASSES = ROWS / RSTEP;
+  static_assert(THREADS % CPR == 0 && ROWS % RSTEP == 0, "tile/thread mismatch");
+  const int col = (tid % CPR) * E, r0 = tid / CPR;
+  const int kbytes = min(max(kvalid - col, 0), E) * 8;
 #pragma unroll
-    for (int c = tid; c < ROWS * CPR; c += THREADS) {
-      int r = c / CPR, col = (c % CPR) * 2;
-      const double* g = row_ptr(r);
-      int valid = g ? min(max(col_limit - col, 0), 2) : 0;
-      cp_async16(s + r * PITCH + col, valid ? (g + col) : dummy, valid * 8);
-    }
-  } else {
+  for (int i = 0; i < PASSES; ++i) {
+    const int r = r0 + i * RSTEP;
+    const int bytes = r < rows_valid ? kbytes : 0;
+    cp_async<E>(s + r * PITCH + col, bytes ? g + (long long)r * ld + col : dummy, bytes);
+  }
+}
+//   "KN": tile rows = K, tile columns = N (or M) index (contiguous); gcol / cbytes are the per-thread global column
+//   offset and valid byte count of its column group (they encode the (s,y) grouping of the NN operator mode)
+template <int COLS, int PITCH, int THREADS, int E>
+__device__ __forceinline__ void load_kn(double* s, const double* g, long long ld, int kvalid, int gcol, int cbytes, int tid,
+                                        const double* dummy) {
+  constexpr int CPR = COLS / E, RSTEP = THREADS / CPR, PASSES = BK / RSTEP;
+  static_assert(THREADS % CPR == 0 && BK % RSTEP == 0, "tile/thread mismatch");
+  const int col = (tid % CPR) * E, r0 = tid / CPR;
 #pragma unroll
-    for (int c = tid; c < ROWS * COLS; c += THREADS) {
-      int r = c / COLS, col = c % COLS;
-      const double* g = row_ptr(r);
-      int valid = (g && col < col_limit) ? 1 : 0;
-      cp_async8(s + r * PITCH + col, valid ? (g + col) : dummy, valid * 8);
-    }
+  for (int i = 0; i < PASSES; ++i) {
+    const int r = r0 + i * RSTEP;
+    const int bytes = r < kvalid ? cbytes : 0;
+    cp_async<E>(s + r * PITCH + col, bytes ? g + (long long)r * ld + gcol : dummy, bytes);
   }
 }
 
@@ -97,7 +108,9 @@ __global__ void __launch_bounds__(Cfg::THREADS) chain_gemm_kernel(const GemmPara
   using SL = SmemLayout<Cfg, MODE>;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, WM = Cfg::WM, WN = Cfg::WN, STAGES = Cfg::STAGES;
   constexpr int MT = Cfg::MT, NT = Cfg::NT, THREADS = Cfg::THREADS;
+  constexpr int E = A16 ? 2 : 1;
   extern __shared__ __align__(16) double smem[];
+  double* const sOpRing = smem + SL::STAGE_ELEMS * STAGES;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int warp_m = warp % Cfg::WARPS_M, warp_n = warp / Cfg::WARPS_M;
@@ -106,6 +119,7 @@ __global__ void __launch_bounds__(Cfg::THREADS) chain_gemm_kernel(const GemmPara
   const int BNy = (MODE == TN_NN && d > 1) ? ((BN / d) / 8) * 8 : BN;  // y values per tile (NN); N = d*Ny
   const int BMe = (MODE == TN_NT && d > 1) ? (BM / d) * d : BM;        // rows per tile (NT)
   const int Ny = (MODE == TN_NN && d > 1) ? p.N / d : p.N;
+  const double* const dummy = reinterpret_cast<const double*>(p.links);  // valid global address for zero-byte copies
 
   // per-thread constants of the fragment <-> tile mapping
   int m_s[MT], m_base[MT];  // NT: physical index s of fragment row, first row of its (x, :) group
@@ -121,7 +135,7 @@ __global__ void __launch_bounds__(Cfg::THREADS) chain_gemm_kernel(const GemmPara
     int c = warp_n * WN + nt * 8 + g;
     int s = (MODE == TN_NN && d > 1) ? c / BNy : 0;
     n_y[nt] = (MODE == TN_NN && d > 1) ? c % BNy : c;
-    n_s[nt] = s < d ? s : 0;  // columns beyond d*BNy are computed on garbage-free data and discarded
+    n_s[nt] = s < d ? s : 0;  // columns beyond d*BNy hold zeros and their results are discarded
   }
 
   long long w, w_end;
@@ -158,132 +172,131 @@ __global__ void __launch_bounds__(Cfg::THREADS) chain_gemm_kernel(const GemmPara
     const int m0 = tm * BMe;
     const int n0 = tnn * BNy;  // NN with d>1: first y of the tile; otherwise first column
 
+    // per-thread column group of the "KN" tiles (constant over the k loop)
+    int a_gcol = 0, a_cbytes = 0, b_gcol = 0, b_cbytes = 0;
+    if (MODE == TN_TN) {
+      const int col = (tid % (BM / E)) * E;
+      a_gcol = m0 + col;
+      a_cbytes = min(max(p.M - m0 - col, 0), E) * 8;
+    }
+    if (MODE != TN_NT) {
+      const int col = (tid % (BN / E)) * E;
+      if (MODE == TN_NN && d > 1) {
+        const int s = col / BNy, y = col % BNy;
+        b_gcol = s * Ny + n0 + y;
+        b_cbytes = (s < d) ? min(max(min(Ny - n0, BNy) - y, 0), E) * 8 : 0;
+      } else {
+        b_gcol = n0 + col;
+        b_cbytes = min(max(p.N - n0 - col, 0), E) * 8;
+      }
+    }
+    const int a_rows_valid = min(BMe, p.M - m0);  // MK tiles of A
+    const int b_rows_valid = min(BN, p.N - n0);   // MK tile of B (NT)
+
     double acc[MT][NT][2];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
-    // ---- producer: issue the copies of iteration it (relative to the link chain of this problem) ----
-    auto issue = [&](int stage, int it) {
+    int li_cached = -1;
+    const double *Ag = nullptr, *Bg = nullptr;
+
+    // ---- producer: the copies of iteration `it` of this problem's link chain; inactive -> zero-byte copies ----
+    auto issue = [&](int stage, int it, bool active) {
       const int li = P.link_begin + it / p.ipl;
       const int k0 = (it % p.ipl) * BK;
-      const LinkDev* L = p.links + li;
-      const double* Ag = L->a_dyn ? p.dyn_in : L->A;
-      const double* Bg = L->b_dyn ? p.dyn_in : L->B;
+      if (active && li != li_cached) {  // rare, CTA-uniform
+        const LinkDev* L = p.links + li;
+        Ag = L->a_dyn ? p.dyn_in : L->A;
+        Bg = L->b_dyn ? p.dyn_in : L->B;
+        if (tid < 16) sOpRing[(li & 3) * 16 + tid] = tid < kMaxD * kMaxD ? L->op[tid] : (tid == 15 ? (double)L->has_op : 0.0);
+        li_cached = li;
+      }
       double* sA = smem + stage * SL::STAGE_ELEMS;
       double* sB = sA + SL::A_ELEMS;
-      if (tid < 16) {  // operator + flag of this stage's link
-        double* sO = sB + SL::B_ELEMS;
-        sO[tid] = tid < kMaxD * kMaxD ? L->op[tid] : (tid == 15 ? (double)L->has_op : 0.0);
-      }
-      const int klim = p.K - k0;
-      const double* dummy = reinterpret_cast<const double*>(p.links);  // valid global address for zero-byte copies
-      if (MODE == TN_TN) {
-        // A tile: BK rows (k) x BM cols (m) of A[(k0+r)*lda + m0 + c]
-        load_tile<BK, BM, SL::A_PITCH, THREADS, A16>(
-            sA, [&](int r) { return r < klim ? Ag + (size_t)(k0 + r) * p.lda + m0 : nullptr; }, p.M - m0, tid, dummy);
-      } else {
-        // A tile: BM rows (m) x BK cols (k)
-        load_tile<BM, BK, SL::A_PITCH, THREADS, A16>(
-            sA,
-            [&](int r) { return (r < BMe && m0 + r < p.M) ? Ag + (size_t)(m0 + r) * p.lda + k0 : nullptr; },
-            klim, tid, dummy);
-      }
-      if (MODE == TN_NT) {
-        // B tile: BN rows (n) x BK cols (k)
-        load_tile<BN, BK, SL::B_PITCH, THREADS, A16>(
-            sB, [&](int r) { return (n0 + r < p.N) ? Bg + (size_t)(n0 + r) * p.ldb + k0 : nullptr; }, klim, tid, dummy);
-      } else if (MODE == TN_NN && d > 1) {
-        // B tile: BK rows (k) x (s, y) cols; group s occupies tile columns [s*BNy, (s+1)*BNy)
-        for (int s = 0; s < d; ++s) {
-          double* sBs = sB + s * BNy;
-          const double* Bs = Bg + (size_t)s * Ny + n0;
-          const int ylim = min(Ny - n0, BNy);
-          if (A16) {
-            const int cpr = BNy / 2;
-            for (int c = tid; c < BK * cpr; c += THREADS) {
-              int r = c / cpr, col = (c % cpr) * 2;
-              int valid = r < klim ? min(max(ylim - col, 0), 2) : 0;
-              cp_async16(sBs + r * SL::B_PITCH + col,
-                         valid ? (Bs + (size_t)(k0 + r) * p.ldb + col) : dummy, valid * 8);
-            }
-          } else {
-            for (int c = tid; c < BK * BNy; c += THREADS) {
-              int r = c / BNy, col = c % BNy;
-              int valid = (r < klim && col < ylim) ? 1 : 0;
-              cp_async8(sBs + r * SL::B_PITCH + col,
-                        valid ? (Bs + (size_t)(k0 + r) * p.ldb + col) : dummy, valid * 8);
-            }
-          }
-        }
-      } else {
-        // B tile: BK rows (k) x BN cols (n)
-        load_tile<BK, BN, SL::B_PITCH, THREADS, A16>(
-            sB, [&](int r) { return r < klim ? Bg + (size_t)(k0 + r) * p.ldb + n0 : nullptr; }, p.N - n0, tid, dummy);
-      }
+      const int kvalid = active ? p.K - k0 : 0;
+      const double* Aq = active ? Ag : dummy;
+      const double* Bq = active ? Bg : dummy;
+      if (MODE == TN_TN)
+        load_kn<BM, SL::A_PITCH, THREADS, E>(sA, Aq + (long long)k0 * p.lda, p.lda, kvalid, a_gcol, a_cbytes, tid, dummy);
+      else
+        load_mk<BM, SL::A_PITCH, THREADS, E>(sA, Aq + (long long)m0 * p.lda + k0, p.lda, a_rows_valid, kvalid, tid, dummy);
+      if (MODE == TN_NT)
+        load_mk<BN, SL::B_PITCH, THREADS, E>(sB, Bq + (long long)n0 * p.ldb + k0, p.ldb, b_rows_valid, kvalid, tid, dummy);
+      else
+        load_kn<BN, SL::B_PITCH, THREADS, E>(sB, Bq + (long long)k0 * p.ldb, p.ldb, kvalid, b_gcol, b_cbytes, tid, dummy);
     };
 
-    // ---- consumer: DMMA over one staged k-block ----
-    auto compute = [&](int stage) {
-      const double* sA = smem + stage * SL::STAGE_ELEMS;
-      const double* sB = sA + SL::A_ELEMS;
-      const double* sO = sB + SL::B_ELEMS;
-      const bool has_op = (d > 1) && (sO[15] != 0.0);
+    // ---- consumer: DMMA over one k4 slice of a staged k-block ----
+    auto compute_kk = [&](const double* sA, const double* sB, const double* sO, const bool has_op, const int kk) {
+      const int kc = kk * 4 + t;
+      double a[MT], b[NT];
 #pragma unroll
-      for (int kk = 0; kk < BK / 4; ++kk) {
-        const int kc = kk * 4 + t;
-        double a[MT], b[NT];
+      for (int mt = 0; mt < MT; ++mt) {
+        const int r = warp_m * WM + mt * 8 + g;
+        if (MODE == TN_TN) {
+          a[mt] = sA[kc * SL::A_PITCH + r];
+        } else if (MODE == TN_NT && has_op) {
+          double v = 0.0;
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          const int r = warp_m * WM + mt * 8 + g;
-          if (MODE == TN_TN) {
-            a[mt] = sA[kc * SL::A_PITCH + r];
-          } else if (MODE == TN_NT && has_op) {
-            double v = 0.0;
-#pragma unroll
-            for (int sp = 0; sp < kMaxD; ++sp)
-              if (sp < d) v += sO[m_s[mt] * d + sp] * sA[(m_base[mt] + sp) * SL::A_PITCH + kc];
-            a[mt] = v;
-          } else {
-            a[mt] = sA[r * SL::A_PITCH + kc];
-          }
+          for (int sp = 0; sp < kMaxD; ++sp)
+            if (sp < d) v += sO[m_s[mt] * d + sp] * sA[(m_base[mt] + sp) * SL::A_PITCH + kc];
+          a[mt] = v;
+        } else {
+          a[mt] = sA[r * SL::A_PITCH + kc];
         }
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          const int c = warp_n * WN + nt * 8 + g;
-          if (MODE == TN_NT) {
-            b[nt] = sB[c * SL::B_PITCH + kc];
-          } else if (MODE == TN_NN && has_op) {
-            double v = 0.0;
-#pragma unroll
-            for (int sp = 0; sp < kMaxD; ++sp)
-              if (sp < d) v += sO[n_s[nt] * d + sp] * sB[kc * SL::B_PITCH + sp * BNy + n_y[nt]];
-            b[nt] = v;
-          } else {
-            b[nt] = sB[kc * SL::B_PITCH + c];
-          }
-        }
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-          for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt], a[mt], b[nt]);
       }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int c = warp_n * WN + nt * 8 + g;
+        if (MODE == TN_NT) {
+          b[nt] = sB[c * SL::B_PITCH + kc];
+        } else if (MODE == TN_NN && has_op) {
+          double v = 0.0;
+#pragma unroll
+          for (int sp = 0; sp < kMaxD; ++sp)
+            if (sp < d) v += sO[n_s[nt] * d + sp] * sB[kc * SL::B_PITCH + sp * BNy + n_y[nt]];
+          b[nt] = v;
+        } else {
+          b[nt] = sB[kc * SL::B_PITCH + c];
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt], a[mt], b[nt]);
     };
 
-    // ---- software pipeline ----
+    // ---- software pipeline: the copies of iteration jj+STAGES-1 are issued between the k4 slices of iteration jj ----
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-      if (s < n_it) issue(s, i0 + s);
+      issue(s, i0 + s, s < n_it);
       cp_async_commit();
     }
     for (int jj = 0; jj < n_it; ++jj) {
       cp_async_wait<STAGES - 2>();
       __syncthreads();
+      const int stage = jj % STAGES;
+      const double* sA = smem + stage * SL::STAGE_ELEMS;
+      const double* sB = sA + SL::A_ELEMS;
+      const int lj = P.link_begin + (i0 + jj) / p.ipl;
+      const double* sO = sOpRing + (lj & 3) * 16;
+      const bool has_op = (d > 1) && (MODE != TN_TN) && (sO[15] != 0.0);
       const int nxt = jj + STAGES - 1;
-      if (nxt < n_it) issue(nxt % STAGES, i0 + nxt);
-      cp_async_commit();
-      compute(jj % STAGES);
+      if (has_op) {
+        compute_kk(sA, sB, sO, true, 0);
+        issue(nxt % STAGES, i0 + nxt, nxt < n_it);
+        cp_async_commit();
+#pragma unroll
+        for (int kk = 1; kk < BK / 4; ++kk) compute_kk(sA, sB, sO, true, kk);
+      } else {
+        compute_kk(sA, sB, sO, false, 0);
+        issue(nxt % STAGES, i0 + nxt, nxt < n_it);
+        cp_async_commit();
+#pragma unroll
+        for (int kk = 1; kk < BK / 4; ++kk) compute_kk(sA, sB, sO, false, kk);
+      }
     }
     cp_async_wait<0>();
     __syncthreads();
