@@ -24,7 +24,15 @@
 
 namespace tn {
 
-constexpr int BK = 16;
+// tile configuration of the large path; the defaults are the best of the variants measured on B200
+// (profiles/r01_kernel_variants.md): 128x64 CTA tile, BK = 32, 2 stages, two independent CTAs per SM (ping-pong)
+#ifndef TN_BK
+#define TN_BK 32
+#endif
+#ifndef TN_STAGES_L
+#define TN_STAGES_L 2
+#endif
+constexpr int BK = TN_BK;
 constexpr int PAD = 4;
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
@@ -48,8 +56,9 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-template <int BM_, int BN_, int WM_, int WN_, int STAGES_>
+template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int MINB_ = 1>
 struct TileCfg {
+  static constexpr int MINB = MINB_;
   static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_;
   static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
   static constexpr int THREADS = WARPS_M * WARPS_N * 32;
@@ -104,7 +113,7 @@ __device__ __forceinline__ void load_kn(double* s, const double* g, long long ld
 }
 
 template <class Cfg, int MODE, bool A16>
-__global__ void __launch_bounds__(Cfg::THREADS) chain_gemm_kernel(const GemmParams p) {
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) chain_gemm_kernel(const GemmParams p) {
   using SL = SmemLayout<Cfg, MODE>;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, WM = Cfg::WM, WN = Cfg::WN, STAGES = Cfg::STAGES;
   constexpr int MT = Cfg::MT, NT = Cfg::NT, THREADS = Cfg::THREADS;
@@ -343,8 +352,20 @@ __global__ void __launch_bounds__(Cfg::THREADS) chain_gemm_kernel(const GemmPara
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-using CfgL = TileCfg<128, 128, 32, 64, 4>;  // 256 threads, 64 accumulator doubles per thread
-using CfgS = TileCfg<64, 64, 32, 32, 4>;    // 128 threads, 32 accumulator doubles per thread
+#ifndef TN_CFGL_WN
+#define TN_CFGL_WN 64
+#endif
+#ifndef TN_CFGL_BM
+#define TN_CFGL_BM 128
+#endif
+#ifndef TN_CFGL_BN
+#define TN_CFGL_BN 64
+#endif
+#ifndef TN_CFGL_CTAS
+#define TN_CFGL_CTAS 2
+#endif
+using CfgL = TileCfg<TN_CFGL_BM, TN_CFGL_BN, 32, TN_CFGL_WN, TN_STAGES_L, TN_CFGL_CTAS>;  // default: 4 warps of 32x64, 64 accumulator doubles per thread
+using CfgS = TileCfg<64, 64, 32, 32, (TN_BK > 16 ? 3 : 4)>;    // 128 threads, 32 accumulator doubles per thread
 
 template <class Cfg, int MODE, bool A16>
 static int launch_one(const GemmParams& p, int grid, cudaStream_t stream) {
@@ -428,7 +449,7 @@ int gemm_plan_schedule(const GemmLaunch& L, ProblemDev* problems, const LinkDev*
   S->tiles_n = large ? tnL : tnS;
   S->ipl = ipl;
   const int tiles = S->tiles_m * S->tiles_n;
-  const int ctas_per_sm = large ? 1 : 2;
+  const int ctas_per_sm = large ? TN_CFGL_CTAS : 2;
   const int max_grid = sms * ctas_per_sm;
 
   long long work = 0, tile_acc = 0, max_tile_iters = 0;
