@@ -15,16 +15,52 @@ from scipy.linalg import eigh_tridiagonal
 from oracle import dmrg_oracle as orc
 
 
+def shard_groups(g, rank, world):
+    """round-robin ownership of the links in the order HL, LS.., HR, RS.., X.. (tn_effh_plan_create); the on-site part
+    belongs to rank 0"""
+    if world <= 1:
+        return g
+    out = {k: (list(v) if isinstance(v, list) else v) for k, v in g.items()}
+    idx = 0
+
+    def own():
+        nonlocal idx
+        mine = idx % world == rank
+        idx += 1
+        return mine
+    if not own():
+        out['HL'] = None
+    keep = [own() for _ in g['LS']]
+    out['LS'] = [x for x, k in zip(g['LS'], keep) if k]
+    out['ls_ops'] = [x for x, k in zip(g['ls_ops'], keep) if k]
+    if not own():
+        out['HR'] = None
+    keep = [own() for _ in g['RS']]
+    out['RS'] = [x for x, k in zip(g['RS'], keep) if k]
+    out['rs_ops'] = [x for x, k in zip(g['rs_ops'], keep) if k]
+    keep = [own() for _ in g['XL']]
+    for key in ('XL', 'XR', 'x_coeff'):
+        out[key] = [x for x, k in zip(g[key], keep) if k]
+    if rank != 0:
+        out['M'] = None
+    return out
+
+
 class CpuPlan:
-    def __init__(self, shape, g):
+    def __init__(self, shape, g, rank=0, world=1):
         self.shape = shape
-        self.g = g
+        self.rank, self.world = rank, world
         a, d, b = shape
-        kl = (1 if g['HL'] is not None else 0) + len(g['LS'])
-        kr = (1 if g['HR'] is not None else 0) + len(g['RS'])
-        nx = len(g['XL'])
+        full = g
+        g = shard_groups(g, rank, world)
+        self.g = g
+        self._full = full
+        kl = (1 if full['HL'] is not None else 0) + len(full['LS'])
+        kr = (1 if full['HR'] is not None else 0) + len(full['RS'])
+        nx = len(full['XL'])
         self.flops_algorithmic = 2.0 * a * d * b * (a * (kl + nx) + b * (kr + nx))
-        self.flops_executed = self.flops_algorithmic
+        self.flops_executed = 2.0 * a * d * b * (a * ((1 if g['HL'] is not None else 0) + len(g['LS']) + len(g['XL'])) +
+                                                 b * ((1 if g['HR'] is not None else 0) + len(g['RS']) + len(g['XL'])))
         self._handle = self
 
     def apply(self, x):
@@ -47,7 +83,7 @@ class CpuPlan:
 
     def matvec(self, psi, c_id=0.0, c_h=1.0, out=None):
         x = psi.numpy().reshape(-1)
-        y = c_id * x + c_h * self.apply(x)
+        y = (c_id * x if self.rank == 0 else 0.0) + c_h * self.apply(x)
         return torch.from_numpy(y.reshape(psi.shape))
 
     def destroy(self):
@@ -113,7 +149,7 @@ class CpuBackend:
         g = {'HL': n(HL), 'HR': n(HR), 'M': None if M is None else np.asarray(M), 'LS': [n(t) for t in LS],
              'ls_ops': [np.asarray(o) for o in ls_ops], 'RS': [n(t) for t in RS], 'rs_ops': [np.asarray(o) for o in rs_ops],
              'XL': [n(t) for t in XL], 'XR': [n(t) for t in XR], 'x_coeff': list(x_coeff)}
-        return CpuPlan(tuple(shape), g)
+        return CpuPlan(tuple(shape), g, rank, world)
 
     def lanczos(self, plan, tau, v0, tol, ncv=20, max_restarts=1000, allreduce=None):
         """numpy transcription of tn_lanczos_lm1 (tnalg_b200/csrc/lanczos.cu)."""
@@ -129,8 +165,10 @@ class CpuBackend:
         for cycle in range(max_restarts):
             m_eff = m
             for j in range(j0, m):
-                w = plan.apply(V[j])
+                w = np.ascontiguousarray(plan.apply(V[j]))
                 n_mv += 1
+                if allreduce is not None:
+                    assert allreduce(w.ctypes.data, w.size, None, None) == 0
                 h = V[:j + 1] @ w
                 w = w - V[:j + 1].T @ h
                 h2 = V[:j + 1] @ w

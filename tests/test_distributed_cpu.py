@@ -1,0 +1,69 @@
+"""N > 1 path on CPU: two gloo ranks shard the coupling-term links of every matvec, all-reduce H|psi> once per
+Lanczos step and must stay in lock-step (same energies on both ranks, equal to the reference golden)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, case, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from tests.cpu_backend import CpuBackend
+        from tests.test_host_logic_cpu import para_from_golden
+        from tnalg_b200 import ops
+        from tnalg_b200.DMRG_anyH import dmrg_finite_size
+        ops.set_backend(CpuBackend())
+        g = dict(np.load(os.path.join(ROOT, 'tests', 'golden', case + '.npz')))
+        para = para_from_golden(g)
+        np.random.seed(int(g['seed']))
+        ob, A, info, para = dmrg_finite_size(para)
+        q.put((rank, float(ob['e_per_site'][0]), ob['mz'].reshape(-1).tolist(), [lm.tolist() for lm in A.lm],
+               info['flops_executed'] / info['flops_algorithmic']))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('case', ['e2e_j1j2_4x2'])
+def test_two_ranks_shard_terms_and_agree(case):
+    world, port = 2, 29500 + os.getpid() % 2000
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = dict(np.load(os.path.join(ROOT, 'tests', 'golden', case + '.npz')))
+    (r0, e0, mz0, lm0, f0), (r1, e1, mz1, lm1, f1) = res
+    assert e0 == e1 and mz0 == mz1 and lm0 == lm1            # replicas stay bit-identical
+    assert abs(e0 - g['e_per_site'][0]) <= 1e-10 * abs(g['e_per_site'][0])
+    assert np.abs(np.array(mz0) - g['mz'].reshape(-1)).max() < 1e-8
+    for n, lm in enumerate(lm0):
+        assert np.abs(np.array(lm) - g['lm_%d' % n]).max() <= 1e-10 * g['lm_%d' % n].max() + 1e-12
+    assert 0.3 < f0 < 0.8 and 0.3 < f1 < 0.8                    # each rank executed about half of the link flops
+
+
+def test_sharded_plans_sum_to_full_operator():
+    from tests.cpu_backend import CpuPlan
+    rng = np.random.RandomState(0)
+    a, d, b = 5, 2, 6
+    g = {'HL': rng.randn(a, a), 'HR': rng.randn(b, b), 'M': rng.randn(d, d), 'LS': [rng.randn(a, a) for _ in range(3)],
+         'ls_ops': [rng.randn(d, d) for _ in range(3)], 'RS': [rng.randn(b, b) for _ in range(2)],
+         'rs_ops': [rng.randn(d, d) for _ in range(2)], 'XL': [rng.randn(a, a) for _ in range(4)],
+         'XR': [rng.randn(b, b) for _ in range(4)], 'x_coeff': list(rng.randn(4))}
+    x = torch.from_numpy(rng.randn(a, d, b))
+    full = CpuPlan((a, d, b), g).matvec(x, 1.0, -0.3).numpy()
+    for world in (2, 3, 8):
+        parts = sum(CpuPlan((a, d, b), g, r, world).matvec(x, 1.0, -0.3).numpy() for r in range(world))
+        assert np.abs(parts - full).max() < 1e-13

@@ -423,6 +423,10 @@ class MpsOpenBoundaryClass(MpsBasic):
 def _alias_tensor(ptr, count, device):
     """torch view of `count` float64 values at device address `ptr` (used by the all-reduce callback)."""
     import torch
+    if torch.device(device).type == 'cpu':  # host logic tests (gloo): alias ordinary memory
+        import ctypes
+        buf = (ctypes.c_double * int(count)).from_address(int(ptr))
+        return torch.from_numpy(np.ctypeslib.as_array(buf))
 
     class _Holder:
         pass
