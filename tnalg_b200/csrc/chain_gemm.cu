@@ -208,33 +208,79 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) chain_gemm_kernel(con
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
-    int li_cached = -1;
-    const double *Ag = nullptr, *Bg = nullptr;
+    // ---- per-thread copy geometry (pass 0); pass i adds i * RSTEP rows ----
+    constexpr int A_CPR = SL::A_COLS / E, A_RSTEP = THREADS / A_CPR, A_PASSES = SL::A_ROWS / A_RSTEP;
+    constexpr int B_CPR = SL::B_COLS / E, B_RSTEP = THREADS / B_CPR, B_PASSES = SL::B_ROWS / B_RSTEP;
+    const int a_r0 = tid / A_CPR, a_col = (tid % A_CPR) * E;
+    const int b_r0 = tid / B_CPR, b_col = (tid % B_CPR) * E;
+    // element offset of this thread's first copy relative to the operand base at k-block 0, advance per k-block
+    const long long a_off0 = (MODE == TN_TN) ? (long long)a_r0 * p.lda + a_gcol : (long long)(m0 + a_r0) * p.lda + a_col;
+    const long long b_off0 = (MODE == TN_NT) ? (long long)(n0 + b_r0) * p.ldb + b_col : (long long)b_r0 * p.ldb + b_gcol;
+    const long long a_kadv = (MODE == TN_TN) ? (long long)BK * p.lda : BK;
+    const long long b_kadv = (MODE == TN_NT) ? BK : (long long)BK * p.ldb;
+    const long long a_pstride = (long long)A_RSTEP * p.lda, b_pstride = (long long)B_RSTEP * p.ldb;
+    const int a_soff = a_r0 * SL::A_PITCH + a_col, b_soff = b_r0 * SL::B_PITCH + b_col;
+    // interior tile: every copy of every k-block is a full, in-range 8*E-byte copy -> no predicates, pointer increments only
+    bool fast = (p.K % BK == 0);
+    if (MODE == TN_TN) fast = fast && (p.M - m0 >= BM); else fast = fast && (a_rows_valid == BM);
+    if (MODE == TN_NT) fast = fast && (b_rows_valid == BN);
+    else if (MODE == TN_NN && d > 1) fast = fast && (d * BNy == BN) && (Ny - n0 >= BNy);
+    else fast = fast && (p.N - n0 >= BN);
 
-    // ---- producer: the copies of iteration `it` of this problem's link chain; inactive -> zero-byte copies ----
-    auto issue = [&](int stage, int it, bool active) {
-      const int li = P.link_begin + it / p.ipl;
-      const int k0 = (it % p.ipl) * BK;
-      if (active && li != li_cached) {  // rare, CTA-uniform
-        const LinkDev* L = p.links + li;
-        Ag = L->a_dyn ? p.dyn_in : L->A;
-        Bg = L->b_dyn ? p.dyn_in : L->B;
-        if (tid < 16) sOpRing[(li & 3) * 16 + tid] = tid < kMaxD * kMaxD ? L->op[tid] : (tid == 15 ? (double)L->has_op : 0.0);
-        li_cached = li;
+    // ---- producer / consumer positions inside the link chain, advanced incrementally ----
+    int p_link = P.link_begin + i0 / p.ipl, p_k = i0 % p.ipl, p_left = n_it;
+    int c_k = p_k, c_link = p_link;
+    int li_cached = -1;
+    const double *Ag = nullptr, *Bg = nullptr;  // operand bases of the cached link
+    const double *pa = nullptr, *pb = nullptr;  // fast path: this thread's pass-0 source pointers for the next k-block
+
+    auto issue = [&](int stage) {
+      if (p_left > 0) {  // CTA-uniform
+        if (p_link != li_cached) {  // rare: first k-block of a link
+          const LinkDev* L = p.links + p_link;
+          Ag = L->a_dyn ? p.dyn_in : L->A;
+          Bg = L->b_dyn ? p.dyn_in : L->B;
+          if (tid < 16) sOpRing[(p_link & 3) * 16 + tid] = tid < kMaxD * kMaxD ? L->op[tid] : (tid == 15 ? (double)L->has_op : 0.0);
+          li_cached = p_link;
+          pa = Ag + a_off0 + p_k * a_kadv;
+          pb = Bg + b_off0 + p_k * b_kadv;
+        }
+        double* sA = smem + stage * SL::STAGE_ELEMS;
+        double* sB = sA + SL::A_ELEMS;
+        if (fast) {
+          const double* q = pa;
+#pragma unroll
+          for (int i = 0; i < A_PASSES; ++i) {
+            cp_async<E>(sA + a_soff + i * A_RSTEP * SL::A_PITCH, q, E * 8);
+            q += a_pstride;
+          }
+          q = pb;
+#pragma unroll
+          for (int i = 0; i < B_PASSES; ++i) {
+            cp_async<E>(sB + b_soff + i * B_RSTEP * SL::B_PITCH, q, E * 8);
+            q += b_pstride;
+          }
+          pa += a_kadv;
+          pb += b_kadv;
+        } else {
+          const int k0 = p_k * BK;
+          const int kvalid = p.K - k0;
+          if (MODE == TN_TN)
+            load_kn<BM, SL::A_PITCH, THREADS, E>(sA, Ag + (long long)k0 * p.lda, p.lda, kvalid, a_gcol, a_cbytes, tid, dummy);
+          else
+            load_mk<BM, SL::A_PITCH, THREADS, E>(sA, Ag + (long long)m0 * p.lda + k0, p.lda, a_rows_valid, kvalid, tid, dummy);
+          if (MODE == TN_NT)
+            load_mk<BN, SL::B_PITCH, THREADS, E>(sB, Bg + (long long)n0 * p.ldb + k0, p.ldb, b_rows_valid, kvalid, tid, dummy);
+          else
+            load_kn<BN, SL::B_PITCH, THREADS, E>(sB, Bg + (long long)k0 * p.ldb, p.ldb, kvalid, b_gcol, b_cbytes, tid, dummy);
+        }
+        if (++p_k == p.ipl) {
+          p_k = 0;
+          ++p_link;
+        }
+        --p_left;
       }
-      double* sA = smem + stage * SL::STAGE_ELEMS;
-      double* sB = sA + SL::A_ELEMS;
-      const int kvalid = active ? p.K - k0 : 0;
-      const double* Aq = active ? Ag : dummy;
-      const double* Bq = active ? Bg : dummy;
-      if (MODE == TN_TN)
-        load_kn<BM, SL::A_PITCH, THREADS, E>(sA, Aq + (long long)k0 * p.lda, p.lda, kvalid, a_gcol, a_cbytes, tid, dummy);
-      else
-        load_mk<BM, SL::A_PITCH, THREADS, E>(sA, Aq + (long long)m0 * p.lda + k0, p.lda, a_rows_valid, kvalid, tid, dummy);
-      if (MODE == TN_NT)
-        load_mk<BN, SL::B_PITCH, THREADS, E>(sB, Bq + (long long)n0 * p.ldb + k0, p.ldb, b_rows_valid, kvalid, tid, dummy);
-      else
-        load_kn<BN, SL::B_PITCH, THREADS, E>(sB, Bq + (long long)k0 * p.ldb, p.ldb, kvalid, b_gcol, b_cbytes, tid, dummy);
+      cp_async_commit();
     };
 
     // ---- consumer: DMMA over one k4 slice of a staged k-block ----
@@ -277,32 +323,34 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) chain_gemm_kernel(con
         for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt], a[mt], b[nt]);
     };
 
-    // ---- software pipeline: the copies of iteration jj+STAGES-1 are issued between the k4 slices of iteration jj ----
+    // ---- software pipeline: the copies of k-block jj+STAGES-1 are issued between the k4 slices of k-block jj ----
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
-      issue(s, i0 + s, s < n_it);
-      cp_async_commit();
-    }
+    for (int s = 0; s < STAGES - 1; ++s) issue(s);
+    const double* sO = sOpRing;
+    bool has_op = false;
     for (int jj = 0; jj < n_it; ++jj) {
       cp_async_wait<STAGES - 2>();
       __syncthreads();
       const int stage = jj % STAGES;
       const double* sA = smem + stage * SL::STAGE_ELEMS;
       const double* sB = sA + SL::A_ELEMS;
-      const int lj = P.link_begin + (i0 + jj) / p.ipl;
-      const double* sO = sOpRing + (lj & 3) * 16;
-      const bool has_op = (d > 1) && (MODE != TN_TN) && (sO[15] != 0.0);
-      const int nxt = jj + STAGES - 1;
+      if (jj == 0 || c_k == 0) {  // first k-block of a link: pick up its operator
+        sO = sOpRing + (c_link & 3) * 16;
+        has_op = (d > 1) && (MODE != TN_TN) && (sO[15] != 0.0);
+      }
+      if (++c_k == p.ipl) {
+        c_k = 0;
+        ++c_link;
+      }
+      const int nstage = (jj + STAGES - 1) % STAGES;
       if (has_op) {
         compute_kk(sA, sB, sO, true, 0);
-        issue(nxt % STAGES, i0 + nxt, nxt < n_it);
-        cp_async_commit();
+        issue(nstage);
 #pragma unroll
         for (int kk = 1; kk < BK / 4; ++kk) compute_kk(sA, sB, sO, true, kk);
       } else {
         compute_kk(sA, sB, sO, false, 0);
-        issue(nxt % STAGES, i0 + nxt, nxt < n_it);
-        cp_async_commit();
+        issue(nstage);
 #pragma unroll
         for (int kk = 1; kk < BK / 4; ++kk) compute_kk(sA, sB, sO, false, kk);
       }
@@ -313,7 +361,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) chain_gemm_kernel(con
     // ---- epilogue ----
     double* Cg = P.c_dyn ? p.dyn_out : P.C;
     const double alpha = P.c_dyn ? P.alpha * p.dyn_alpha : P.alpha;
-    const bool atomic = p.split != 0;
+    const bool atomic = p.split != 0 || P.shared_out != 0;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
       const int r = warp_m * WM + mt * 8 + g;
@@ -540,7 +588,7 @@ extern "C" int tn_chain_gemm(int mode, int M, int N, int K, int d, int lda, int 
   for (int q = 0; q < n_problems; ++q) {
     ph[q].C = problems[q].C; ph[q].alpha = problems[q].alpha;
     ph[q].link_begin = problems[q].link_begin; ph[q].link_count = problems[q].link_count;
-    ph[q].accumulate = problems[q].accumulate; ph[q].c_dyn = 0;
+    ph[q].accumulate = problems[q].accumulate; ph[q].c_dyn = 0; ph[q].shared_out = 0; ph[q].pad = 0;
   }
   GemmLaunch L{mode, M, N, K, d, lda, ldb, ldc, n_problems, n_links, deterministic};
   GemmSchedule S;

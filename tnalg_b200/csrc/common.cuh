@@ -85,6 +85,8 @@ struct ProblemDev {
   int link_begin, link_count;
   int accumulate;
   int c_dyn;             // 1: C = params.dyn_out and alpha is multiplied by params.dyn_alpha
+  int shared_out;        // 1: other problems of this launch add into the same C -> always combine with FP64 atomics
+  int pad;
   long long work_begin;  // prefix sum of tiles*iters (stream-K) over the problems of the launch
   long long tile_begin;  // prefix sum of tiles
 };

@@ -38,7 +38,7 @@ static bool owns(int idx, int rank, int world) { return world <= 1 || idx % worl
 extern "C" size_t tn_effh_plan_workspace_bytes(int a, int d, int b, int n_ls, int n_rs, int n_x) {
   size_t n = (size_t)a * d * b;
   return align_up(sizeof(ProblemDev) * (size_t)(1 + n_x)) + align_up(sizeof(LinkDev) * (size_t)(1 + n_ls + n_x)) +
-         align_up(sizeof(ProblemDev)) + align_up(sizeof(LinkDev) * (size_t)(1 + n_rs + n_x)) +
+         align_up(sizeof(ProblemDev) * (size_t)(1 + n_rs + n_x)) + align_up(sizeof(LinkDev) * (size_t)(1 + n_rs + n_x)) +
          align_up(sizeof(double) * n * (size_t)std::max(n_x, 0)) + 1024;
 }
 
@@ -81,7 +81,7 @@ extern "C" int tn_effh_plan_create(tn_effh_plan** out_plan, int a, int d, int b,
   Carver cw(workspace, workspace_bytes);
   P->probA = cw.take<ProblemDev>(1 + n_x);
   P->linkA = cw.take<LinkDev>(1 + n_ls + n_x);
-  P->probB = cw.take<ProblemDev>(1);
+  P->probB = cw.take<ProblemDev>(1 + n_rs + n_x);
   P->linkB = cw.take<LinkDev>(1 + n_rs + n_x);
   P->phi = cw.take<double>((size_t)P->n * std::max(n_x, 0) + 1);
   if (!P->probA || !P->linkA || !P->probB || !P->linkB || !P->phi) {
@@ -140,13 +140,22 @@ extern "C" int tn_effh_plan_create(tn_effh_plan** out_plan, int a, int d, int b,
     TN_CUDA(cudaMemcpyAsync(P->linkA, la.data(), sizeof(LinkDev) * la.size(), cudaMemcpyHostToDevice, stream));
   }
   if (P->haveB) {
-    ProblemDev q{};
-    q.C = nullptr; q.alpha = 1.0; q.link_begin = 0; q.link_count = (int)lb.size(); q.accumulate = 1; q.c_dyn = 1;
-    pb.push_back(q);
-    P->LB = GemmLaunch{TN_NT, a * d, b, b, d, b, b, b, 1, (int)lb.size(), 0};
+    // The right stage is one long chain (K_R + n_x links) into `out`.  It is cut into sub-problems of kChunk links that
+    // all add into `out` with FP64 atomics: tiles are then visited chunk by chunk, every CTA of the grid works on the same
+    // few links at the same time and their operands (Phi_i, XR_i) are shared through L2 instead of being re-read from HBM
+    // by every tile (17.9 GB -> ~1.5 GB of DRAM reads per launch at chi = 1024, profiles/r01_ncu_matvec.md).
+    const int kChunk = 3;
+    const int nl = (int)lb.size();
+    for (int l0 = 0; l0 < nl; l0 += kChunk) {
+      ProblemDev q{};
+      q.C = nullptr; q.alpha = 1.0; q.link_begin = l0; q.link_count = std::min(kChunk, nl - l0); q.accumulate = 1; q.c_dyn = 1;
+      q.shared_out = nl > kChunk ? 1 : 0;
+      pb.push_back(q);
+    }
+    P->LB = GemmLaunch{TN_NT, a * d, b, b, d, b, b, b, (int)pb.size(), nl, 0};
     int st = gemm_plan_schedule(P->LB, pb.data(), lb.data(), fake_psi, fake_psi, &P->SB);
     if (st != TN_OK) { delete P; return st; }
-    TN_CUDA(cudaMemcpyAsync(P->probB, pb.data(), sizeof(ProblemDev), cudaMemcpyHostToDevice, stream));
+    TN_CUDA(cudaMemcpyAsync(P->probB, pb.data(), sizeof(ProblemDev) * pb.size(), cudaMemcpyHostToDevice, stream));
     TN_CUDA(cudaMemcpyAsync(P->linkB, lb.data(), sizeof(LinkDev) * lb.size(), cudaMemcpyHostToDevice, stream));
   }
   const double KL = (HL ? 1 : 0) + n_ls, KR = (HR ? 1 : 0) + n_rs;
