@@ -19,7 +19,13 @@ TN_HD inline double tn_sign(double a, double b) { return b >= 0.0 ? fabs(a) : -f
 //   d[0..n)  diagonal in, eigenvalues out (unsorted);  e[i] couples i and i+1 (e[n-1] ignored, destroyed);
 //   z (n x n, row-major, leading dimension ldz) must hold the identity on entry; column k is the eigenvector of d[k].
 // Returns 0 on success, 1 when an eigenvalue needed more than 60 iterations.
-TN_HD inline int tridiag_ql(int n, double* d, double* e, double* z, int ldz) {
+// Rows k = k0, k0 + kstride, ... of z are updated by the caller: the scalar recurrences are deterministic, so several
+// threads may run the routine redundantly on private copies of d/e while each owns a subset of the rows of a shared z
+// (lanczos_ritz_kernel: one lane per row).  (k0, kstride) = (0, 1) is the plain serial routine.
+TN_HD inline int tridiag_ql_rows(int n, double* d, double* e, double* z, int ldz, int k0, int kstride);
+TN_HD inline int tridiag_ql(int n, double* d, double* e, double* z, int ldz) { return tridiag_ql_rows(n, d, e, z, ldz, 0, 1); }
+
+TN_HD inline int tridiag_ql_rows(int n, double* d, double* e, double* z, int ldz, int k0, int kstride) {
   if (n <= 0) return 0;
   e[n - 1] = 0.0;
   for (int l = 0; l < n; ++l) {
@@ -54,7 +60,7 @@ TN_HD inline int tridiag_ql(int n, double* d, double* e, double* z, int ldz) {
           p = s * r;
           d[i + 1] = g + p;
           g = c * r - b;
-          for (int k = 0; k < n; ++k) {
+          for (int k = k0; k < n; k += kstride) {
             f = z[k * ldz + i + 1];
             z[k * ldz + i + 1] = s * z[k * ldz + i] + c * f;
             z[k * ldz + i] = c * z[k * ldz + i] - s * f;

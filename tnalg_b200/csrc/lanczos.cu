@@ -8,11 +8,16 @@
 // alpha/beta, the projected tridiagonal eigenproblem, the Ritz selection and the convergence flag live in a small
 // device struct; the host only enqueues kernels and reads one 64-byte status record per restart cycle.
 #include <cmath>
+#include <cstdlib>
 #include <vector>
+
+#include <cooperative_groups.h>
 
 #include "common.cuh"
 #include "host_math.h"
 #include "vector_ops.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace tn {
 long long plan_dim(const tn_effh_plan* P);
@@ -61,25 +66,33 @@ __global__ void lanczos_finish_step_kernel(LanczosState* st, int j) {
 }
 
 // projected eigenproblem of dimension m (or m_eff after a breakdown); selects the Ritz value maximising |1 - tau*theta|
-__global__ void lanczos_ritz_kernel(LanczosState* st, int m_in, double tau, double tol) {
-  __shared__ double d[kMaxNcv], e[kMaxNcv], z[kMaxNcv * kMaxNcv];
-  if (threadIdx.x != 0) return;
+__global__ void __launch_bounds__(32) lanczos_ritz_kernel(LanczosState* st, int m_in, double tau, double tol) {
+  // one warp: every lane runs the scalar QL recurrences on private copies of (d, e); lane k owns rows k, k+32 of z
+  constexpr int LDZ = kMaxNcv + 1;  // odd pitch: conflict-free row access
+  __shared__ double z[kMaxNcv * LDZ];
+  const int lane = threadIdx.x;
+  double d[kMaxNcv], e[kMaxNcv];
   const int m = st->breakdown ? st->m_eff : m_in;
   for (int i = 0; i < m; ++i) {
     d[i] = st->alpha[i];
     e[i] = st->beta[i];
-    for (int k = 0; k < m; ++k) z[i * m + k] = (i == k) ? 1.0 : 0.0;
   }
+  for (int i = lane; i < m; i += 32)
+    for (int k = 0; k < m; ++k) z[i * LDZ + k] = (i == k) ? 1.0 : 0.0;
+  __syncwarp();
   const double beta_last = st->breakdown ? 0.0 : st->beta[m - 1];
-  st->ql_fail = tridiag_ql(m, d, e, z, m);
+  const int fail = tridiag_ql_rows(m, d, e, z, LDZ, lane, 32);
+  __syncwarp();
   int best = 0;
   for (int k = 1; k < m; ++k)
     if (fabs(1.0 - tau * d[k]) > fabs(1.0 - tau * d[best])) best = k;
+  if (lane != 0) return;
   double nrm = 0.0;
-  for (int i = 0; i < m; ++i) nrm += z[i * m + best] * z[i * m + best];
+  for (int i = 0; i < m; ++i) nrm += z[i * LDZ + best] * z[i * LDZ + best];
   nrm = sqrt(nrm);
-  for (int i = 0; i < kMaxNcv; ++i) st->u[i] = i < m ? z[i * m + best] / nrm : 0.0;
+  for (int i = 0; i < kMaxNcv; ++i) st->u[i] = i < m ? z[i * LDZ + best] / nrm : 0.0;
   const double s = beta_last * st->u[m - 1];
+  st->ql_fail = fail;
   st->theta = d[best];
   st->lambda = 1.0 - tau * d[best];
   st->s_restart = s;
@@ -96,6 +109,147 @@ __global__ void lanczos_restart_kernel(LanczosState* st) {
   st->breakdown = 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Fused re-orthogonalisation step for vectors that live in L2 (n <= kFusedMaxN): one cooperative launch replaces the
+// seven launches of the streaming path.  Every CTA owns a contiguous slice of the vector, keeps its slice of w in shared
+// memory across the phases, and the grid meets at three grid-wide barriers:
+//   phase 1  h  = V^T w            (warp-per-vector dots over the slice, warp-shuffle reduction)   -> sync
+//   phase 2  w -= V h ; h2 = V^T w                                                                 -> sync
+//   phase 3  w -= V h2 ; |w|^2                                                                     -> sync
+//   phase 4  alpha_j, beta_j, breakdown test (same arithmetic as lanczos_finish_step_kernel); w *= 1/beta, written back
+// Partial sums are combined in CTA order by every CTA, so the result is bit-reproducible and identical in all CTAs.
+constexpr int kFusedThreads = 256;
+constexpr long long kFusedMaxN = 1LL << 19;       // 4 MiB vectors: 22 of them stay L2 resident
+
+__device__ __forceinline__ double warp_sum_l(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(kFusedThreads) lanczos_orth_fused_kernel(double* __restrict__ V, long long ldv, int j, long long n,
+                                                                           LanczosState* st, double* __restrict__ partial,
+                                                                           int slice_cap, int cache_v) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) double dyn[];
+  double* ws = dyn;              // this CTA's slice of w (slice_cap doubles)
+  double* vs = dyn + slice_cap;  // cache_v: this CTA's slice of v_0..v_j, row pitch slice_cap
+  __shared__ double hs[kMaxNcv + 1];
+  __shared__ double red[kFusedThreads / 32];
+  const int nb = gridDim.x, b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nvec = j + 1;
+  const long long chunk = (n + nb - 1) / nb;
+  const long long e0 = min((long long)b * chunk, n);
+  const int len = (int)(min(e0 + chunk, n) - e0);
+  double* w = V + (long long)(j + 1) * ldv + e0;
+  const double* Vg = V + e0;
+  for (int e = tid; e < len; e += kFusedThreads) ws[e] = w[e];
+  if (cache_v) {  // one coalesced pass over the basis slice; all later phases run out of shared memory
+    for (int i = 0; i < nvec; ++i) {
+      const double* v = Vg + (long long)i * ldv;
+      for (int e = tid; e < len; e += kFusedThreads) vs[i * slice_cap + e] = v[e];
+    }
+  }
+  __syncthreads();
+  const double* Vs = cache_v ? vs : Vg;
+  const long long vpitch = cache_v ? (long long)slice_cap : ldv;
+
+  auto dots = [&](double* out /* nb x (kMaxNcv+1) */) {
+    for (int i = warp; i < nvec; i += kFusedThreads / 32) {
+      const double* v = Vs + (long long)i * vpitch;
+      double acc0 = 0.0, acc1 = 0.0;
+      int e = lane;
+      for (; e + 32 < len; e += 64) {
+        acc0 += v[e] * ws[e];
+        acc1 += v[e + 32] * ws[e + 32];
+      }
+      if (e < len) acc0 += v[e] * ws[e];
+      const double acc = warp_sum_l(acc0 + acc1);
+      if (lane == 0) out[(long long)b * (kMaxNcv + 1) + i] = acc;
+    }
+  };
+  auto gather = [&](const double* in) {  // hs[i] = sum over CTAs: lane-strided partial sums + fixed shuffle tree (same in all CTAs)
+    __syncthreads();
+    for (int i = warp; i < nvec; i += kFusedThreads / 32) {
+      double s = 0.0;
+      for (int c = lane; c < nb; c += 32) s += in[(long long)c * (kMaxNcv + 1) + i];
+      s = warp_sum_l(s);
+      if (lane == 0) hs[i] = s;
+    }
+    __syncthreads();
+  };
+  auto update = [&]() {  // ws -= sum_i hs[i] * V_i
+    for (int e = tid; e < len; e += kFusedThreads) {
+      double v0 = ws[e], v1 = 0.0;
+      int i = 0;
+      for (; i + 1 < nvec; i += 2) {
+        v0 -= hs[i] * Vs[(long long)i * vpitch + e];
+        v1 -= hs[i + 1] * Vs[(long long)(i + 1) * vpitch + e];
+      }
+      if (i < nvec) v0 -= hs[i] * Vs[(long long)i * vpitch + e];
+      ws[e] = v0 + v1;
+    }
+    __syncthreads();
+  };
+  double* p1 = partial;
+  double* p2 = partial + (long long)nb * (kMaxNcv + 1);
+  double* p3 = p2 + (long long)nb * (kMaxNcv + 1);
+
+  dots(p1);
+  grid.sync();
+  gather(p1);
+  const double h_j = hs[j];
+  update();
+  dots(p2);
+  grid.sync();
+  gather(p2);
+  const double h2_j = hs[j];
+  update();
+  {
+    double acc = 0.0;
+    for (int e = tid; e < len; e += kFusedThreads) acc += ws[e] * ws[e];
+    acc = warp_sum_l(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < kFusedThreads / 32; ++k) s += red[k];
+      p3[b] = s;
+    }
+  }
+  grid.sync();
+  double nrm2 = 0.0;
+  for (int c = lane; c < nb; c += 32) nrm2 += p3[c];
+  nrm2 = warp_sum_l(nrm2);  // every warp of every CTA computes the same value
+  // bookkeeping, identical in every thread of every CTA (reads are of values written before this launch)
+  const double a = h_j + h2_j;
+  const double bj = sqrt(nrm2);
+  double scale = fabs(a);
+  if (j > 0) scale = fmax(scale, fabs(st->beta[j - 1]));
+  scale = fmax(scale, 1e-300);
+  const int was_broken = st->breakdown;
+  const bool broken = was_broken || bj <= 1e-14 * scale;
+  const double inv = broken ? 0.0 : 1.0 / bj;
+  for (int e = tid; e < len; e += kFusedThreads) w[e] = ws[e] * inv;
+  grid.sync();  // every CTA has read st->breakdown / beta[j-1] before CTA 0 updates the state
+  if (b == 0 && tid == 0) {
+    st->alpha[j] = a;
+    st->beta[j] = bj;
+    st->nrm2 = nrm2;
+    if (broken) {
+      if (!was_broken) {
+        st->breakdown = 1;
+        st->m_eff = j + 1;
+        st->beta[j] = 0.0;
+      }
+      st->inv_beta = 0.0;
+    } else {
+      st->inv_beta = inv;
+    }
+  }
+}
+
 struct LanczosStatus {
   double theta, resid, lambda, s_restart;
   int converged, breakdown, m_eff, ql_fail;
@@ -108,7 +262,8 @@ using namespace tn;
 extern "C" size_t tn_lanczos_workspace_bytes(long long n, int ncv) {
   const long long m = std::min<long long>(std::max(ncv, 2), std::min<long long>(n, kMaxNcv));
   const size_t ldv = (size_t)((n + 1) / 2 * 2);
-  return align_up(sizeof(double) * ldv * (size_t)(m + 2)) + align_up(sizeof(double) * (size_t)(m + 1) * dot_chunks(n)) +
+  return align_up(sizeof(double) * ldv * (size_t)(m + 2)) +
+         align_up(sizeof(double) * std::max<size_t>((size_t)(m + 1) * dot_chunks(n), (size_t)3 * 2048 * (kMaxNcv + 1))) +
          align_up(sizeof(LanczosState)) + align_up(sizeof(unsigned)) + 1024;
 }
 
@@ -129,7 +284,7 @@ extern "C" int tn_lanczos_lm1(tn_effh_plan* plan, double tau, const double* v0, 
   const long long ldv = (n + 1) / 2 * 2;
   Carver cw(workspace, workspace_bytes);
   double* V = cw.take<double>((size_t)ldv * (m + 2));
-  double* partial = cw.take<double>((size_t)(m + 1) * dot_chunks(n));
+  double* partial = cw.take<double>(std::max<size_t>((size_t)(m + 1) * dot_chunks(n), (size_t)3 * 2048 * (kMaxNcv + 1)));
   LanczosState* st = cw.take<LanczosState>(1);
   unsigned* counter = cw.take<unsigned>(1);
   TN_REQUIRE(V && partial && st && counter, "tn_lanczos_lm1: workspace carve failed");
@@ -145,6 +300,29 @@ extern "C" int tn_lanczos_lm1(tn_effh_plan* plan, double tau, const double* v0, 
   TN_LAUNCHED();
   TN_CHECK(launch_scale_dev(vec(0), &st->inv_beta, n, stream));
 
+  // fused cooperative re-orthogonalisation when the vectors are L2 resident and a slice fits the shared-memory buffer
+  int fused_grid = 0, fused_slice = 0, fused_cache = 0;
+  size_t fused_smem = 0;
+  if (n <= kFusedMaxN && !getenv("TNALG_NO_FUSED_ORTH")) {
+    const int sms = sm_count();
+    // preferred: one CTA per SM with the CTA's slice of the whole basis cached in shared memory
+    const int grid1 = (int)std::max<long long>(1, std::min<long long>(sms, (n + 511) / 512));
+    const int slice1 = (int)(((n + grid1 - 1) / grid1 + 1) / 2 * 2);
+    const size_t smem1 = sizeof(double) * (size_t)slice1 * (size_t)(m + 2);
+    if (smem1 <= 200 * 1024) {
+      fused_grid = grid1; fused_slice = slice1; fused_cache = 1; fused_smem = smem1;
+    }  // larger vectors: the streaming kernels (more CTAs in flight) are faster than an uncached fused pass
+    if (fused_grid > 0) {
+      static size_t configured = 0;
+      if (fused_smem > configured) {
+        TN_CUDA(cudaFuncSetAttribute(lanczos_orth_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        configured = 200 * 1024;
+      }
+      int per_sm = 0;
+      TN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lanczos_orth_fused_kernel, kFusedThreads, fused_smem));
+      if (per_sm * sms < fused_grid) fused_grid = 0;  // cannot be co-resident: use the streaming path
+    }
+  }
   int n_matvec = 0;
   int j0 = 0;
   LanczosStatus hs{};
@@ -158,15 +336,26 @@ extern "C" int tn_lanczos_lm1(tn_effh_plan* plan, double tau, const double* v0, 
         int rc = allreduce(w, n, allreduce_user, stream);
         TN_REQUIRE(rc == 0, "tn_lanczos_lm1: all-reduce callback failed (%d)", rc);
       }
-      // CGS2 against v_0..v_j
-      TN_CHECK(launch_multidot(V, ldv, j + 1, w, n, st->h, partial, counter, stream));
-      TN_CHECK(launch_multi_axpy(w, V, ldv, j + 1, st->h, n, stream));
-      TN_CHECK(launch_multidot(V, ldv, j + 1, w, n, st->h2, partial, counter, stream));
-      TN_CHECK(launch_multi_axpy(w, V, ldv, j + 1, st->h2, n, stream));
-      TN_CHECK(launch_multidot(w, ldv, 1, w, n, &st->nrm2, partial, counter, stream));
-      lanczos_finish_step_kernel<<<1, 1, 0, stream>>>(st, j);
-      TN_LAUNCHED();
-      TN_CHECK(launch_scale_dev(w, &st->inv_beta, n, stream));
+      if (fused_grid > 0) {
+        // one cooperative launch: CGS2, norm, scale and the alpha/beta bookkeeping of step j
+        long long ldv_arg = ldv, n_arg = n;
+        int j_arg = j;
+        void* args[] = {(void*)&V, (void*)&ldv_arg, (void*)&j_arg, (void*)&n_arg, (void*)&st, (void*)&partial,
+                        (void*)&fused_slice, (void*)&fused_cache};
+        TN_CUDA(cudaLaunchCooperativeKernel((const void*)lanczos_orth_fused_kernel, dim3(fused_grid), dim3(kFusedThreads), args,
+                                            fused_smem, stream));
+        TN_LAUNCHED();
+      } else {
+        // streaming path (HBM-bound kernels): CGS2 against v_0..v_j, norm, bookkeeping, scale
+        TN_CHECK(launch_multidot(V, ldv, j + 1, w, n, st->h, partial, counter, stream));
+        TN_CHECK(launch_multi_axpy(w, V, ldv, j + 1, st->h, n, stream));
+        TN_CHECK(launch_multidot(V, ldv, j + 1, w, n, st->h2, partial, counter, stream));
+        TN_CHECK(launch_multi_axpy(w, V, ldv, j + 1, st->h2, n, stream));
+        TN_CHECK(launch_multidot(w, ldv, 1, w, n, &st->nrm2, partial, counter, stream));
+        lanczos_finish_step_kernel<<<1, 1, 0, stream>>>(st, j);
+        TN_LAUNCHED();
+        TN_CHECK(launch_scale_dev(w, &st->inv_beta, n, stream));
+      }
     }
     lanczos_ritz_kernel<<<1, 32, 0, stream>>>(st, m, tau, tol);
     TN_LAUNCHED();
