@@ -76,6 +76,8 @@ struct LinkDev {
   int has_op;
   int a_dyn;  // 1: A = params.dyn_in (psi of this matvec call)
   int b_dyn;  // 1: B = params.dyn_in
+  int a_map;  // TMA path: index of the operand's tensor map in the plan's map table (unused when a_dyn)
+  int b_map;
   int pad;
 };
 

@@ -12,7 +12,10 @@
 #include <cstring>
 #include <vector>
 
+#include <cstdlib>
+
 #include "common.cuh"
+#include "tma.cuh"
 #include "vector_ops.cuh"
 
 using namespace tn;
@@ -31,6 +34,9 @@ struct tn_effh_plan {
   double* phi;
   int n_phi;
   double alg_flops, exec_flops;
+  // TMA staging (chain_gemm_tma.cu): tensor maps of the fixed operands; psi maps are encoded per call
+  bool tmaA, tmaB;
+  TmaMap* maps;
 };
 
 static bool owns(int idx, int rank, int world) { return world <= 1 || idx % world == rank; }
@@ -39,7 +45,7 @@ extern "C" size_t tn_effh_plan_workspace_bytes(int a, int d, int b, int n_ls, in
   size_t n = (size_t)a * d * b;
   return align_up(sizeof(ProblemDev) * (size_t)(1 + n_x)) + align_up(sizeof(LinkDev) * (size_t)(1 + n_ls + n_x)) +
          align_up(sizeof(ProblemDev) * (size_t)(1 + n_rs + n_x)) + align_up(sizeof(LinkDev) * (size_t)(1 + n_rs + n_x)) +
-         align_up(sizeof(double) * n * (size_t)std::max(n_x, 0)) + 1024;
+         align_up(sizeof(double) * n * (size_t)std::max(n_x, 0)) + align_up(sizeof(TmaMap) * (size_t)(3 * (2 + n_ls + n_rs + 2 * n_x))) + 1024;
 }
 
 static void set_link(LinkDev& L, const double* A, const double* B, int a_dyn, int b_dyn, const double* op, int d) {
@@ -84,7 +90,9 @@ extern "C" int tn_effh_plan_create(tn_effh_plan** out_plan, int a, int d, int b,
   P->probB = cw.take<ProblemDev>(1 + n_rs + n_x);
   P->linkB = cw.take<LinkDev>(1 + n_rs + n_x);
   P->phi = cw.take<double>((size_t)P->n * std::max(n_x, 0) + 1);
-  if (!P->probA || !P->linkA || !P->probB || !P->linkB || !P->phi) {
+  P->maps = cw.take<TmaMap>((size_t)(3 * (2 + n_ls + n_rs + 2 * n_x)));
+  P->tmaA = P->tmaB = false;
+  if (!P->probA || !P->linkA || !P->probB || !P->linkB || !P->phi || !P->maps) {
     delete P;
     set_error("tn_effh_plan_create: workspace carve failed");
     return TN_ERR_WORKSPACE;
@@ -132,10 +140,20 @@ extern "C" int tn_effh_plan_create(tn_effh_plan** out_plan, int a, int d, int b,
   P->haveA = !pa.empty();
   P->haveB = !lb.empty();
   const double* fake_psi = reinterpret_cast<const double*>(uintptr_t(256));  // alignment stand-in for scheduling
+  const bool use_tma = tma_available() && !getenv("TNALG_NO_TMA");
+  std::vector<TmaMap> hmaps;
   if (P->haveA) {
     P->LA = GemmLaunch{TN_NN, a, d * b, a, d, a, d * b, d * b, (int)pa.size(), (int)la.size(), 0};
     int st = gemm_plan_schedule(P->LA, pa.data(), la.data(), fake_psi, fake_psi, &P->SA);
     if (st != TN_OK) { delete P; return st; }
+    if (use_tma && P->SA.config == 0 && P->SA.aligned16) {  // left stage: A = environment matrix (a x a), B = psi (per call)
+      P->tmaA = true;
+      for (auto& l : la) {
+        l.a_map = (int)hmaps.size();
+        hmaps.emplace_back();
+        if (tma_encode_2d(&hmaps.back(), l.A, a, a, a, tma_box_rows_a()) != TN_OK) { P->tmaA = false; break; }
+      }
+    }
     TN_CUDA(cudaMemcpyAsync(P->probA, pa.data(), sizeof(ProblemDev) * pa.size(), cudaMemcpyHostToDevice, stream));
     TN_CUDA(cudaMemcpyAsync(P->linkA, la.data(), sizeof(LinkDev) * la.size(), cudaMemcpyHostToDevice, stream));
   }
@@ -155,9 +173,24 @@ extern "C" int tn_effh_plan_create(tn_effh_plan** out_plan, int a, int d, int b,
     P->LB = GemmLaunch{TN_NT, a * d, b, b, d, b, b, b, (int)pb.size(), nl, 0};
     int st = gemm_plan_schedule(P->LB, pb.data(), lb.data(), fake_psi, fake_psi, &P->SB);
     if (st != TN_OK) { delete P; return st; }
+    if (use_tma && P->SB.config == 0 && P->SB.aligned16) {  // right stage: A = psi (per call) or Phi_i, B = environment matrix (b x b)
+      P->tmaB = true;
+      for (auto& l : lb) {
+        if (!l.a_dyn) {
+          l.a_map = (int)hmaps.size();
+          hmaps.emplace_back();
+          if (tma_encode_2d(&hmaps.back(), l.A, (long long)a * d, b, b, tma_box_rows_a()) != TN_OK) { P->tmaB = false; break; }
+        }
+        l.b_map = (int)hmaps.size();
+        hmaps.emplace_back();
+        if (tma_encode_2d(&hmaps.back(), l.B, b, b, b, tma_box_rows_b_nt()) != TN_OK) { P->tmaB = false; break; }
+      }
+    }
     TN_CUDA(cudaMemcpyAsync(P->probB, pb.data(), sizeof(ProblemDev) * pb.size(), cudaMemcpyHostToDevice, stream));
     TN_CUDA(cudaMemcpyAsync(P->linkB, lb.data(), sizeof(LinkDev) * lb.size(), cudaMemcpyHostToDevice, stream));
   }
+  if (!hmaps.empty() && (P->tmaA || P->tmaB))
+    TN_CUDA(cudaMemcpyAsync(P->maps, hmaps.data(), sizeof(TmaMap) * hmaps.size(), cudaMemcpyHostToDevice, stream));
   const double KL = (HL ? 1 : 0) + n_ls, KR = (HR ? 1 : 0) + n_rs;
   P->alg_flops = 2.0 * a * d * b * ((double)a * (KL + n_x) + (double)b * (KR + n_x));
   P->exec_flops = 2.0 * a * d * b * ((double)a * (double)la.size() + (double)b * (double)lb.size());
@@ -175,11 +208,22 @@ extern "C" int tn_effh_matvec(tn_effh_plan* P, const double* psi_in, double* psi
   // identity + on-site part (rank 0 only when sharded); doubles as the zero-initialisation of `out`
   const bool lead = P->rank == 0;
   TN_CHECK(launch_site_op_axpby(psi_out, psi_in, P->a, P->d, P->b, lead ? c_id : 0.0, (lead && P->has_M) ? c_h : 0.0, P->M, stream));
+  TmaMap psi_a, psi_b;  // psi as the A operand of the right stage / the (k, s, y) B operand of the left stage
+  if (P->tmaA) TN_CHECK(tma_encode_3d(&psi_b, psi_in, P->a, P->d, P->b, (long long)P->d * P->b));
+  if (P->tmaB) TN_CHECK(tma_encode_2d(&psi_a, psi_in, (long long)P->a * P->d, P->b, P->b, tma_box_rows_a()));
   if (P->haveA) {
     if (P->SA.split && P->n_phi > 0) TN_CUDA(cudaMemsetAsync(P->phi, 0, sizeof(double) * (size_t)P->n * P->n_phi, stream));
-    TN_CHECK(gemm_launch(P->LA, P->SA, P->probA, P->linkA, psi_in, psi_out, c_h, stream));
+    if (P->tmaA)
+      TN_CHECK(gemm_launch_tma(P->LA, P->SA, P->probA, P->linkA, P->maps, psi_a, psi_b, psi_in, psi_out, c_h, stream));
+    else
+      TN_CHECK(gemm_launch(P->LA, P->SA, P->probA, P->linkA, psi_in, psi_out, c_h, stream));
   }
-  if (P->haveB) TN_CHECK(gemm_launch(P->LB, P->SB, P->probB, P->linkB, psi_in, psi_out, c_h, stream));
+  if (P->haveB) {
+    if (P->tmaB)
+      TN_CHECK(gemm_launch_tma(P->LB, P->SB, P->probB, P->linkB, P->maps, psi_a, psi_b, psi_in, psi_out, c_h, stream));
+    else
+      TN_CHECK(gemm_launch(P->LB, P->SB, P->probB, P->linkB, psi_in, psi_out, c_h, stream));
+  }
   return TN_OK;
 }
 
