@@ -147,6 +147,8 @@ int tn_effh_matvec(tn_effh_plan* plan, const double* psi_in /* [dev] */, double*
                    double c_h, void* stream);
 /* algorithmic flop of one matvec: 2*a*d*b*[a*(K_L+n_x) + b*(K_R+n_x)], and executed flop. */
 int tn_effh_plan_flops(const tn_effh_plan* plan, double* algorithmic, double* executed);
+/* bit 0: the left stage runs the TMA-staged kernel, bit 1: the right stage does (else the cp.async kernel). */
+int tn_effh_plan_uses_tma(const tn_effh_plan* plan);
 int tn_effh_plan_destroy(tn_effh_plan* plan);
 
 /* --------------------------------------------------------------------------------------------------

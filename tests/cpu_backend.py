@@ -62,23 +62,36 @@ class CpuPlan:
         self.flops_executed = 2.0 * a * d * b * (a * ((1 if g['HL'] is not None else 0) + len(g['LS']) + len(g['XL'])) +
                                                  b * ((1 if g['HR'] is not None else 0) + len(g['RS']) + len(g['XL'])))
         self._handle = self
+        self.uses_tma = 0
 
     def apply(self, x):
+        """H_eff x as GEMMs (the formulation of absorb_matrix2tensor, TensorBasicModule.py:387-424)"""
         g = self.g
-        t = x.reshape(self.shape)
+        a, d, b = self.shape
+        t = np.asarray(x).reshape(self.shape)
+
+        def left(mat, y):
+            return (mat @ y.reshape(a, d * b)).reshape(a, d, b)
+
+        def right(mat, y):
+            return (y.reshape(a * d, b) @ mat.T).reshape(a, d, b)
+
+        def mid(op, y):
+            return np.einsum('st,atb->asb', op, y)
+
         out = np.zeros_like(t)
         if g['HL'] is not None:
-            out += np.einsum('ax,xsb->asb', g['HL'], t)
+            out += left(g['HL'], t)
         if g['HR'] is not None:
-            out += np.einsum('asy,by->asb', t, g['HR'])
+            out += right(g['HR'], t)
         if g['M'] is not None:
-            out += np.einsum('st,atb->asb', g['M'], t)
+            out += mid(g['M'], t)
         for E, op in zip(g['LS'], g['ls_ops']):
-            out += np.einsum('ax,st,xtb->asb', E, op, t)
+            out += left(E, mid(op, t))
         for E, op in zip(g['RS'], g['rs_ops']):
-            out += np.einsum('by,st,aty->asb', E, op, t)
+            out += right(E, mid(op, t))
         for c, l, r in zip(g['x_coeff'], g['XL'], g['XR']):
-            out += c * np.einsum('ax,xsy,by->asb', l, t, r)
+            out += c * right(r, left(l, t))
         return out.reshape(-1)
 
     def matvec(self, psi, c_id=0.0, c_h=1.0, out=None):

@@ -193,6 +193,32 @@ def test_matvec_vs_oracle(be, shape, counts):
     assert np.abs(sum(parts) - y).max() < 1e-14 * max(1.0, np.abs(y).max())
 
 
+@pytest.mark.parametrize('shape,counts', [((384, 2, 320), (3, 3, 10)), ((512, 2, 512), (3, 3, 4)), ((300, 2, 260), (2, 3, 9)),
+                                          ((258, 3, 264), (3, 2, 6)), ((640, 2, 192), (3, 3, 0))])
+@pytest.mark.parametrize('tma', [True, False])
+def test_matvec_large_config_vs_oracle(be, shape, counts, tma, monkeypatch):
+    """shapes that are scheduled on the 128x64 configuration: the TMA-staged kernel (default) and the cp.async kernel
+    (TNALG_NO_TMA=1) against the numpy oracle, including ragged edges (zero fill) and d = 3"""
+    from tests.cpu_backend import CpuPlan
+    if not tma:
+        monkeypatch.setenv('TNALG_NO_TMA', '1')
+    else:
+        monkeypatch.delenv('TNALG_NO_TMA', raising=False)
+    rng = np.random.RandomState(sum(shape) + sum(counts))
+    a, d, b = shape
+    g = random_groups(rng, a, d, b, *counts)
+    x = rng.randn(a, d, b)
+    ref = CpuPlan(shape, g).apply(x.reshape(-1))
+    plan = gpu_plan(be, shape, g)
+    assert plan.uses_tma == (3 if tma else 0), 'expected the %s kernel' % ('TMA' if tma else 'cp.async')
+    y = be.to_numpy(plan.matvec(be.from_numpy(x), 0.0, 1.0)).reshape(-1)
+    assert rel_err(y, ref) < 1e-13, (shape, tma)
+    y2 = be.to_numpy(plan.matvec(be.from_numpy(x), 1.0, -0.25)).reshape(-1)
+    assert rel_err(y2, x.reshape(-1) - 0.25 * ref) < 1e-13
+    parts = [be.to_numpy(gpu_plan(be, shape, g, rank=r, world=2).matvec(be.from_numpy(x), 0.0, 1.0)).reshape(-1) for r in range(2)]
+    assert rel_err(sum(parts), ref) < 1e-13
+
+
 def test_matvec_without_any_block(be):
     """a site with only an on-site field (no environment blocks at all) still works"""
     rng = np.random.RandomState(3)

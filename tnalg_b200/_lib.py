@@ -52,6 +52,7 @@ SIGNATURES = {
                                       C.c_void_p, C.c_size_t, C.c_void_p]),
     'tn_effh_matvec': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]),
     'tn_effh_plan_flops': (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
+    'tn_effh_plan_uses_tma': (C.c_int, [C.c_void_p]),
     'tn_effh_plan_destroy': (C.c_int, [C.c_void_p]),
     'tn_lanczos_workspace_bytes': (C.c_size_t, [C.c_longlong, C.c_int]),
     'tn_lanczos_lm1': (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_double, C.c_int, C.c_int, c_double_p,

@@ -26,13 +26,10 @@ namespace tn {
 
 // tile configuration of the large path; the defaults are the best of the variants measured on B200
 // (profiles/r01_kernel_variants.md): 128x64 CTA tile, BK = 32, 2 stages, two independent CTAs per SM (ping-pong)
-#ifndef TN_BK
-#define TN_BK 32
-#endif
 #ifndef TN_STAGES_L
 #define TN_STAGES_L 2
 #endif
-constexpr int BK = TN_BK;
+constexpr int BK = kBK;
 constexpr int PAD = 4;
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {

@@ -25,14 +25,18 @@
 namespace tn {
 
 namespace {
-constexpr int BM = 128, BN = 64, BK = 32, WM = 32, WN = 64, STAGES = 2, THREADS = 128;
+#ifndef TN_TMA_STAGES
+#define TN_TMA_STAGES 2
+#endif
+constexpr int BM = 128, BN = 64, BK = kBK, WM = 32, WN = 64, STAGES = TN_TMA_STAGES, THREADS = 128;
 constexpr int MT = WM / 8, NT = WN / 8;
 constexpr int BOXW = 16;                      // doubles per box row (128 bytes)
 constexpr int A_ELEMS = BM * BK;              // two boxes of BM x 16
 constexpr int B_ELEMS = BN * BK;              // NT: two boxes of BN x 16; NN: four boxes of BK x 16
 constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
 constexpr unsigned STAGE_BYTES = STAGE_ELEMS * sizeof(double);
-constexpr size_t SMEM_BYTES = size_t(STAGE_ELEMS) * STAGES * sizeof(double) + 4 * 16 * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+constexpr int kRing = STAGES + 2;  // operator ring: one slot per k-block in flight
+constexpr size_t SMEM_BYTES = size_t(STAGE_ELEMS) * STAGES * sizeof(double) + kRing * 16 * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
@@ -74,7 +78,7 @@ __global__ void __launch_bounds__(THREADS, 2) chain_gemm_tma_kernel(const GemmPa
   extern __shared__ __align__(1024) double smem[];  // the swizzle pattern is a function of the shared address: 1024-byte aligned base
   if (smem_u32(smem) & 1023u) __trap();
   double* const sOpRing = smem + STAGE_ELEMS * STAGES;
-  uint64_t* const full = reinterpret_cast<uint64_t*>(sOpRing + 4 * 16);
+  uint64_t* const full = reinterpret_cast<uint64_t*>(sOpRing + kRing * 16);
   uint64_t* const empty = full + STAGES;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -118,88 +122,130 @@ __global__ void __launch_bounds__(THREADS, 2) chain_gemm_tma_kernel(const GemmPa
     w = blockIdx.x;
     w_end = p.total_tiles;
   }
-  int prob = 0;
-  unsigned n_fill = 0, n_cons = 0;  // k-blocks filled / consumed by this CTA since kernel start (barrier phases)
+  const long long w_step = p.split ? 0 : (long long)gridDim.x;  // split: segments follow each other; else tile stride
 
-  while (w < w_end) {
-    int tile, i0, n_it;
+  // A work segment = consecutive k-blocks of one output tile.  Producer and consumers walk the same list of segments with
+  // separate cursors: the producer (thread 0) stays STAGES-1 k-blocks ahead ACROSS segment boundaries, so a new tile never
+  // starts with an empty pipeline.
+  struct Segment {
+    long long w;     // position in the work list
+    int prob;        // problem index (monotone)
+    int m0, n0;      // tile origin
+    int link, k;     // next link / k-block inside the link
+    int left;        // k-blocks left in this segment
+    int n_it;        // k-blocks of the segment
+  };
+  auto decode = [&](Segment& sg) {  // sg.w, sg.prob given; fills the rest; returns false past the end
+    if (sg.w >= w_end) return false;
     if (p.split) {
-      while (prob + 1 < p.n_problems && p.problems[prob + 1].work_begin <= w) ++prob;
+      while (sg.prob + 1 < p.n_problems && p.problems[sg.prob + 1].work_begin <= sg.w) ++sg.prob;
     } else {
-      while (prob + 1 < p.n_problems && p.problems[prob + 1].tile_begin <= w) ++prob;
+      while (sg.prob + 1 < p.n_problems && p.problems[sg.prob + 1].tile_begin <= sg.w) ++sg.prob;
     }
-    const ProblemDev P = p.problems[prob];
+    const ProblemDev& P = p.problems[sg.prob];
     const int iters_tile = P.link_count * p.ipl;
+    int tile, i0;
     if (p.split) {
-      long long rem = w - P.work_begin;
+      const long long rem = sg.w - P.work_begin;
       tile = (int)(rem / iters_tile);
       i0 = (int)(rem % iters_tile);
-      n_it = (int)min((long long)(iters_tile - i0), w_end - w);
+      sg.n_it = (int)min((long long)(iters_tile - i0), w_end - sg.w);
     } else {
-      tile = (int)(w - P.tile_begin);
+      tile = (int)(sg.w - P.tile_begin);
       i0 = 0;
-      n_it = iters_tile;
+      sg.n_it = iters_tile;
     }
-    const int tm = tile % p.tiles_m, tnn = tile / p.tiles_m;
-    const int m0 = tm * BMe;
-    const int n0 = tnn * BNy;
+    sg.m0 = (tile % p.tiles_m) * BMe;
+    sg.n0 = (tile / p.tiles_m) * BNy;
+    sg.link = P.link_begin + i0 / p.ipl;
+    sg.k = i0 % p.ipl;
+    sg.left = sg.n_it;
+    return true;
+  };
+  auto next_segment = [&](Segment& sg) {
+    sg.w += p.split ? sg.n_it : w_step;
+    return decode(sg);
+  };
+
+  unsigned n_fill = 0, n_cons = 0;  // k-blocks filled / consumed by this CTA since kernel start (barrier phases, ring slots)
+  Segment ps;                       // producer cursor (thread 0)
+  ps.w = w; ps.prob = 0;
+  bool p_valid = decode(ps);
+  int li_cached = -1;
+  const CUtensorMap *mapA = nullptr, *mapB = nullptr;
+  const LinkDev* Lc = nullptr;
+
+  // ---- producer (thread 0 only): stage one k-block, possibly of a later segment ----
+  auto produce = [&]() {
+    if (!p_valid) return;
+    if (ps.left == 0) {
+      p_valid = next_segment(ps);
+      if (!p_valid) return;
+    }
+    const int stage = n_fill % STAGES;
+    if (n_fill >= STAGES) mbar_wait(&empty[stage], ((n_fill / STAGES) - 1) & 1);
+    if (ps.link != li_cached) {
+      Lc = p.links + ps.link;
+      mapA = Lc->a_dyn ? &psi_map_a : maps + Lc->a_map;
+      mapB = Lc->b_dyn ? &psi_map_b : maps + Lc->b_map;
+      li_cached = ps.link;
+    }
+    {  // operator of this k-block's link, one ring slot per k-block in flight
+      double* ring = sOpRing + (n_fill % kRing) * 16;
+      const bool hop = (d > 1) && Lc->has_op;
+      ring[15] = hop ? 1.0 : 0.0;
+      if (hop) {
+#pragma unroll
+        for (int i = 0; i < kMaxD * kMaxD; ++i) ring[i] = Lc->op[i];
+      }
+    }
+    double* sA = smem + stage * STAGE_ELEMS;
+    double* sB = sA + A_ELEMS;
+    const int k0 = ps.k * BK;
+    mbar_expect_tx(&full[stage], STAGE_BYTES);
+#pragma unroll
+    for (int h = 0; h < BK / BOXW; ++h) tma_2d(sA + h * BM * BOXW, mapA, k0 + h * BOXW, ps.m0, &full[stage]);
+    if (MODE == TN_NT) {
+#pragma unroll
+      for (int h = 0; h < BK / BOXW; ++h) tma_2d(sB + h * BN * BOXW, mapB, k0 + h * BOXW, ps.n0, &full[stage]);
+    } else {
+      // B tile: BK k-rows, BN/16 boxes of 16 columns; box q covers tile columns [16q, 16q+16) = one (s, y) group
+#pragma unroll
+      for (int q = 0; q < BN / BOXW; ++q) {
+        const int c = q * BOXW;
+        const int s = (d > 1) ? c / BNy : 0;
+        const int y = (d > 1) ? c % BNy : c;
+        if (s < d)
+          tma_3d(sB + q * BK * BOXW, mapB, ps.n0 + y, s, k0, &full[stage]);
+        else
+          tma_3d(sB + q * BK * BOXW, mapB, Ny, 0, k0, &full[stage]);  // fully out of range: zero fill, keeps the byte count
+      }
+    }
+    if (++ps.k == p.ipl) {
+      ps.k = 0;
+      ++ps.link;
+    }
+    --ps.left;
+    ++n_fill;
+  };
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) produce();
+  }
+
+  Segment cs;  // consumer cursor (all threads)
+  cs.w = w; cs.prob = 0;
+  bool c_valid = decode(cs);
+  while (c_valid) {
+    const ProblemDev P = p.problems[cs.prob];
+    const int m0 = cs.m0, n0 = cs.n0, n_it = cs.n_it;
 
     double acc[MT][NT][2];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-
-    int p_link = P.link_begin + i0 / p.ipl, p_k = i0 % p.ipl, p_left = n_it;
-    int c_k = p_k, c_link = p_link;
-    int li_cached = -1;
-    const CUtensorMap *mapA = nullptr, *mapB = nullptr;
-
-    // ---- producer (thread 0 only) ----
-    auto produce = [&]() {
-      if (p_left <= 0) return;
-      const int stage = n_fill % STAGES;
-      if (n_fill >= STAGES) mbar_wait(&empty[stage], ((n_fill / STAGES) - 1) & 1);
-      if (p_link != li_cached) {
-        const LinkDev* L = p.links + p_link;
-        mapA = L->a_dyn ? &psi_map_a : maps + L->a_map;
-        mapB = L->b_dyn ? &psi_map_b : maps + L->b_map;
-        double* ring = sOpRing + (p_link & 3) * 16;
-#pragma unroll
-        for (int i = 0; i < kMaxD * kMaxD; ++i) ring[i] = L->op[i];
-        ring[15] = (double)L->has_op;
-        li_cached = p_link;
-      }
-      double* sA = smem + stage * STAGE_ELEMS;
-      double* sB = sA + A_ELEMS;
-      const int k0 = p_k * BK;
-      mbar_expect_tx(&full[stage], STAGE_BYTES);
-      // A tile: rows m0 .. m0+BM, two boxes of 16 k-columns
-      tma_2d(sA, mapA, k0, m0, &full[stage]);
-      tma_2d(sA + BM * BOXW, mapA, k0 + BOXW, m0, &full[stage]);
-      if (MODE == TN_NT) {
-        tma_2d(sB, mapB, k0, n0, &full[stage]);
-        tma_2d(sB + BN * BOXW, mapB, k0 + BOXW, n0, &full[stage]);
-      } else {
-        // B tile: BK k-rows, BN/16 boxes of 16 columns; box q covers tile columns [16q, 16q+16) = (s, y) group
-#pragma unroll
-        for (int q = 0; q < BN / BOXW; ++q) {
-          const int c = q * BOXW;
-          const int s = (d > 1) ? c / BNy : 0;
-          const int y = (d > 1) ? c % BNy : c;
-          if (s < d)
-            tma_3d(sB + q * BK * BOXW, mapB, n0 + y, s, k0, &full[stage]);
-          else
-            tma_3d(sB + q * BK * BOXW, mapB, Ny, 0, k0, &full[stage]);  // fully out of range: zero fill, keeps the byte count
-        }
-      }
-      if (++p_k == p.ipl) {
-        p_k = 0;
-        ++p_link;
-      }
-      --p_left;
-      ++n_fill;
-    };
 
     // ---- consumer: one k4 slice ----
     auto compute_kk = [&](const double* sA, const double* sB, const double* sO, const bool has_op, const int kk) {
@@ -248,27 +294,14 @@ __global__ void __launch_bounds__(THREADS, 2) chain_gemm_tma_kernel(const GemmPa
         for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt], a[mt], b[nt]);
     };
 
-    // ---- pipeline ----
-    if (tid == 0) {
-#pragma unroll
-      for (int s = 0; s < STAGES - 1; ++s) produce();
-    }
-    const double* sO = sOpRing;
-    bool has_op = false;
     for (int jj = 0; jj < n_it; ++jj) {
-      if (tid == 0) produce();  // k-block jj + STAGES - 1
+      if (tid == 0) produce();  // k-block n_cons + STAGES - 1 of this CTA's work list
       const int stage = n_cons % STAGES;
       mbar_wait(&full[stage], (n_cons / STAGES) & 1);
       const double* sA = smem + stage * STAGE_ELEMS;
       const double* sB = sA + A_ELEMS;
-      if (jj == 0 || c_k == 0) {
-        sO = sOpRing + (c_link & 3) * 16;
-        has_op = (d > 1) && (sO[15] != 0.0);
-      }
-      if (++c_k == p.ipl) {
-        c_k = 0;
-        ++c_link;
-      }
+      const double* sO = sOpRing + (n_cons % kRing) * 16;
+      const bool has_op = sO[15] != 0.0;
       if (has_op) {
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) compute_kk(sA, sB, sO, true, kk);
@@ -315,7 +348,7 @@ __global__ void __launch_bounds__(THREADS, 2) chain_gemm_tma_kernel(const GemmPa
         }
       }
     }
-    w += p.split ? n_it : gridDim.x;
+    c_valid = next_segment(cs);
   }
 }
 

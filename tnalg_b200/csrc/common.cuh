@@ -66,6 +66,12 @@ struct Carver {
     if (s_ != TN_OK) return s_; \
   } while (0)
 
+// k-block of every chain-GEMM kernel; the scheduler (ipl = ceil(K / kBK)), the cp.async kernel and the TMA kernel share it
+#ifndef TN_BK
+#define TN_BK 32
+#endif
+constexpr int kBK = TN_BK;
+
 // ---- device-side descriptors of the chain GEMM (built by the host wrappers in chain_gemm.cu) ----
 constexpr int kMaxD = TN_MAX_PHYS_DIM;
 

@@ -234,6 +234,8 @@ extern "C" int tn_effh_plan_flops(const tn_effh_plan* P, double* algorithmic, do
   return TN_OK;
 }
 
+extern "C" int tn_effh_plan_uses_tma(const tn_effh_plan* P) { return P ? ((P->haveA && P->tmaA) ? 1 : 0) | ((P->haveB && P->tmaB) ? 2 : 0) : 0; }
+
 extern "C" int tn_effh_plan_destroy(tn_effh_plan* P) {
   delete P;
   return TN_OK;

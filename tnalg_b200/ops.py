@@ -48,6 +48,7 @@ class EffHPlan:
         alg, ex = C.c_double(), C.c_double()
         L.check(be.lib.tn_effh_plan_flops(handle, C.byref(alg), C.byref(ex)))
         self.flops_algorithmic, self.flops_executed = alg.value, ex.value
+        self.uses_tma = int(be.lib.tn_effh_plan_uses_tma(handle))  # bit 0 left stage, bit 1 right stage
 
     def matvec(self, psi, c_id=0.0, c_h=1.0, out=None):
         """out = c_id*psi + c_h*H_eff psi; (c_id, c_h) = (1, -tau) is the reference handle (MPSClass.py:755-776)."""
