@@ -210,7 +210,10 @@ def test_matvec_large_config_vs_oracle(be, shape, counts, tma, monkeypatch):
     x = rng.randn(a, d, b)
     ref = CpuPlan(shape, g).apply(x.reshape(-1))
     plan = gpu_plan(be, shape, g)
-    assert plan.uses_tma == (3 if tma else 0), 'expected the %s kernel' % ('TMA' if tma else 'cp.async')
+    # both stages are TMA-staged when both are scheduled on the 128x64 configuration; the last shape (no crossing terms,
+    # narrow right bond) legitimately runs its right stage on the small cp.async configuration
+    expect = 0 if not tma else (1 if counts[2] == 0 else 3)
+    assert plan.uses_tma == expect, 'expected kernel mask %d, got %d' % (expect, plan.uses_tma)
     y = be.to_numpy(plan.matvec(be.from_numpy(x), 0.0, 1.0)).reshape(-1)
     assert rel_err(y, ref) < 1e-13, (shape, tma)
     y2 = be.to_numpy(plan.matvec(be.from_numpy(x), 1.0, -0.25)).reshape(-1)
