@@ -51,7 +51,7 @@ def test_two_ranks_shard_terms_and_agree(case):
     assert np.abs(np.array(mz0) - g['mz'].reshape(-1)).max() < 1e-8
     for n, lm in enumerate(lm0):
         assert np.abs(np.array(lm) - g['lm_%d' % n]).max() <= 1e-10 * g['lm_%d' % n].max() + 1e-12
-    assert 0.3 < f0 < 0.8 and 0.3 < f1 < 0.8                    # each rank executed about half of the link flops
+    assert 0.1 < f0 < 0.8 and 0.1 < f1 < 0.8                    # each rank executes only a share of the (merged) link flops
 
 
 def test_sharded_plans_sum_to_full_operator():

@@ -116,6 +116,7 @@ class EnvCache:
         self.lv = 0        # left blocks of bonds 0..lv are valid
         self.rv = length   # right blocks of bonds rv..L are valid
         self.n_bond_moves = 0
+        self.merge_crossing = True   # False: one GEMM link per crossing term, the reference's literal '1_0_1' list
 
     def invalidate_site(self, n):
         """tensor n changed: left blocks of bonds > n and right blocks of bonds <= n are stale"""
@@ -220,18 +221,44 @@ class EnvCache:
         for s, pairs in sorted(t.closing_right(p).items()):
             g['RS'].append(self._lincomb(rb, pairs))
             g['rs_ops'].append(t.ops[s])
-        for c, lk, rk in t.crossing(p):
-            g['XL'].append(lb['O'][lk])
-            g['XR'].append(rb['O'][rk])
-            g['x_coeff'].append(c)
+        # crossing terms ('1_0_1'): sum_i c_i OL[lk_i] (x) OR[rk_i].  Terms sharing an operator on one side are merged
+        # first, sum_i c_i L_k (x) R_i = L_k (x) (sum_i c_i R_i), exactly as the reference merges the partners of a
+        # '1_s_0' key (MPSClass.py:717-728); the side with fewer distinct operators keeps its matrices, the other side
+        # becomes one tn_lincomb per group.  Same operator, fewer GEMM links (42 -> 21 at the widest 6x6 J1-J2 site).
+        cross = t.crossing(p)
+        by_left, by_right = {}, {}
+        for c, lk, rk in cross:
+            by_left.setdefault(lk, []).append((c, rk))
+            by_right.setdefault(rk, []).append((c, lk))
+        if not self.merge_crossing:
+            for c, lk, rk in cross:
+                g['XL'].append(lb['O'][lk])
+                g['XR'].append(rb['O'][rk])
+                g['x_coeff'].append(c)
+        elif len(by_left) <= len(by_right):
+            for lk in sorted(by_left):
+                g['XL'].append(lb['O'][lk])
+                g['XR'].append(self._lincomb(rb, by_left[lk]))
+                g['x_coeff'].append(1.0)
+        else:
+            for rk in sorted(by_right):
+                g['XL'].append(self._lincomb(lb, by_right[rk]))
+                g['XR'].append(rb['O'][rk])
+                g['x_coeff'].append(1.0)
+        g['n_x_reference'] = len(cross)
         return g
 
     def plan(self, p, mps, rank=0, world=1):
         self.ensure(p, mps)
         a, d, b = mps[p].shape
         g = self.groups(p, d)
-        return self.be.effh_plan((a, d, b), g['HL'], g['HR'], g['M'], g['LS'], g['ls_ops'], g['RS'], g['rs_ops'],
+        plan = self.be.effh_plan((a, d, b), g['HL'], g['HR'], g['M'], g['LS'], g['ls_ops'], g['RS'], g['rs_ops'],
                                  g['XL'], g['XR'], g['x_coeff'], rank=rank, world=world)
+        # algorithmic flop of one matvec = the reference's own grouping, whatever the kernel executes
+        kl = (1 if g['HL'] is not None else 0) + len(g['LS'])
+        kr = (1 if g['HR'] is not None else 0) + len(g['RS'])
+        plan.flops_algorithmic = 2.0 * a * d * b * (a * (kl + g['n_x_reference']) + b * (kr + g['n_x_reference']))
+        return plan
 
 
 def expect_products(be, mps, center, ops, terms):
