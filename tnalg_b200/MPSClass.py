@@ -255,6 +255,7 @@ class MpsOpenBoundaryClass(MpsBasic):
             if terms.length > self.length:
                 raise ValueError('coupling terms reference site %d but the MPS has %d sites' % (terms.length - 1, self.length))
             self._env = EnvCache(self._be, terms, self.length)
+            self._env.dist = self._dist()
             self._env_key = key
             self._env_refs = (index1, index2, coeff1, coeff2)  # keep the ids alive
         return self._env

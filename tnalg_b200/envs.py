@@ -117,6 +117,7 @@ class EnvCache:
         self.rv = length   # right blocks of bonds rv..L are valid
         self.n_bond_moves = 0
         self.merge_crossing = True   # False: one GEMM link per crossing term, the reference's literal '1_0_1' list
+        self.dist = None             # torch.distributed module when the outgoing operators of a bond move are sharded over ranks
 
     def invalidate_site(self, n):
         """tensor n changed: left blocks of bonds > n and right blocks of bonds <= n are stale"""
@@ -134,6 +135,25 @@ class EnvCache:
             self.invalidate_site(n)
 
     # ---- bond moves ----
+    def _env_update(self, direction, T, outputs):
+        """tn_env_update for every outgoing operator of a bond; with several ranks each rank computes the operators
+        j = rank (mod world) and broadcasts them, so all ranks end up with bit-identical blocks (one writer per operator)"""
+        dist = self.dist
+        if dist is None or dist.get_world_size() == 1 or len(outputs) < 2:
+            return self.be.env_update(direction, T, outputs)
+        rank, world = dist.get_rank(), dist.get_world_size()
+        mine = [j for j in range(len(outputs)) if j % world == rank]
+        res = [None] * len(outputs)
+        if mine:
+            for j, mat in zip(mine, self.be.env_update(direction, T, [outputs[j] for j in mine])):
+                res[j] = mat
+        e_dim = T.shape[2] if direction == 0 else T.shape[0]
+        for j in range(len(outputs)):
+            if res[j] is None:
+                res[j] = self.be.empty(e_dim, e_dim)
+            dist.broadcast(res[j], src=j % world)
+        return res
+
     def _lincomb(self, block, pairs):
         xs = [block['O'][key] for _, key in pairs]
         cs = [c for c, _ in pairs]
@@ -162,7 +182,7 @@ class EnvCache:
             keys.append(key)
         new = {'H': None, 'O': {}}
         if outputs:
-            res = self.be.env_update(0, T, outputs)
+            res = self._env_update(0, T, outputs)
             for key, mat in zip(keys, res):
                 if key == 'H':
                     new['H'] = mat
@@ -192,7 +212,7 @@ class EnvCache:
             keys.append(key)
         new = {'H': None, 'O': {}}
         if outputs:
-            res = self.be.env_update(1, T, outputs)
+            res = self._env_update(1, T, outputs)
             for key, mat in zip(keys, res):
                 if key == 'H':
                     new['H'] = mat
