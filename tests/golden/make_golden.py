@@ -172,6 +172,9 @@ def pr_fixtures():
         out['%s_para_op' % tag] = np.stack([np.asarray(o, dtype=complex) for o in para['op']])
         out['%s_t_cost' % tag] = info['t_cost']
         out['%s_attrs' % tag] = np.array(sorted(A.__dict__.keys()))
+        out['%s_center' % tag] = int(A.center)
+        for n, t in enumerate(A.mps):
+            out['%s_mps_%d' % (tag, n)] = np.asarray(t)
     return out
 
 

@@ -108,3 +108,26 @@ def test_size_independent_properties_chi64():
     A.correct_orthogonal_center(para['l'] - 1)
     assert np.abs(A.observe_magnetization(3) - mz0).max() < 1e-10
     assert abs(float(A.observe_bond_energy(para['index2'], para['coeff2']).sum()) - energies[-1]) < 1e-9
+
+
+@pytest.mark.parametrize('tag', ['chi16', 'chi24'])
+def test_observables_of_reference_result_pickles(golden, tag):
+    """the MPS stored in the reference's own data_dmrg/*.pr files: the CUDA observable path reproduces the stored
+    magnetisation, bond energies and (via Jacobi SVD) the stored entanglement spectrum"""
+    from tnalg_b200.MPSClass import MpsOpenBoundaryClass
+    g = golden('pr_fixtures')
+    L, d, chi = int(g[tag + '_para_l']), int(g[tag + '_para_d']), int(g[tag + '_para_chi'])
+    ops_ = [np.real(o) if np.abs(np.imag(o)).max() == 0 else o for o in g[tag + '_para_op']]
+    A = MpsOpenBoundaryClass(L, d, chi, operators=ops_)
+    A.load_tensors([g['%s_mps_%d' % (tag, n)] for n in range(L)], int(g[tag + '_center']))
+    assert np.abs(A.observe_magnetization(3).reshape(-1) - g[tag + '_mz'].reshape(-1)).max() < 1e-10
+    assert np.abs(A.observe_magnetization(1).reshape(-1) - g[tag + '_mx'].reshape(-1)).max() < 1e-10
+    eb = A.observe_bond_energy(g[tag + '_para_index2'], g[tag + '_para_coeff2'])
+    assert np.abs(eb.reshape(-1) - g[tag + '_eb_full'].reshape(-1)).max() < 1e-10
+    assert abs(eb.sum() / L - float(g[tag + '_e_per_site'].reshape(-1)[0])) < 1e-10
+    A.calculate_entanglement_spectrum()
+    A.calculate_entanglement_entropy()
+    for n in range(L - 1):
+        ref = g['%s_lm_%d' % (tag, n)]
+        assert np.abs(A.lm[n] - ref).max() <= 1e-10 * ref.max() + 1e-13, n
+    assert np.abs(A.ent.reshape(-1) - g[tag + '_ent'].reshape(-1)).max() < 1e-9

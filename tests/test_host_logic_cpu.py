@@ -176,3 +176,21 @@ def test_term_table_rejects_unsorted_sites():
     ops = [np.eye(2)] * 7
     with pytest.raises(ValueError):
         TermTable(np.zeros((0, 2)), np.array([[3, 1, 3, 3]]), np.zeros(0), np.ones(1), ops, 1e-12)
+
+
+@pytest.mark.parametrize('tag', ['chi16', 'chi24'])
+def test_observables_of_reference_result_pickles(golden, cpu_be, tag):
+    """host logic on the MPS stored in the reference's own data_dmrg/*.pr files (same check as the GPU test)"""
+    from tnalg_b200.MPSClass import MpsOpenBoundaryClass
+    g = golden('pr_fixtures')
+    L, d, chi = int(g[tag + '_para_l']), int(g[tag + '_para_d']), int(g[tag + '_para_chi'])
+    ops_ = [np.real(o) if np.abs(np.imag(o)).max() == 0 else o for o in g[tag + '_para_op']]
+    A = MpsOpenBoundaryClass(L, d, chi, operators=ops_)
+    A.load_tensors([g['%s_mps_%d' % (tag, n)] for n in range(L)], int(g[tag + '_center']))
+    assert np.abs(A.observe_magnetization(3).reshape(-1) - g[tag + '_mz'].reshape(-1)).max() < 1e-10
+    eb = A.observe_bond_energy(g[tag + '_para_index2'], g[tag + '_para_coeff2'])
+    assert np.abs(eb.reshape(-1) - g[tag + '_eb_full'].reshape(-1)).max() < 1e-10
+    A.calculate_entanglement_spectrum()
+    for n in range(L - 1):
+        ref = g['%s_lm_%d' % (tag, n)]
+        assert np.abs(A.lm[n] - ref).max() <= 1e-10 * ref.max() + 1e-13, n
