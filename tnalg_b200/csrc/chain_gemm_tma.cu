@@ -113,6 +113,13 @@ __global__ void __launch_bounds__(THREADS, 2) chain_gemm_tma_kernel(const GemmPa
     n_y[nt] = (MODE == TN_NN && d > 1) ? c % BNy : c;
     n_s[nt] = s < d ? s : 0;
   }
+  int ep_s[NT], ep_y[NT];  // epilogue: (s, y offset) of fragment columns 2t, 2t+1 of each n-tile (NN with an operator grouping)
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int c = 0 + nt * 8 + 2 * t;
+    ep_s[nt] = (MODE == TN_NN && d > 1) ? c / BNy : 0;
+    ep_y[nt] = (MODE == TN_NN && d > 1) ? c % BNy : c;
+  }
 
   long long w, w_end;
   if (p.split) {
@@ -315,36 +322,44 @@ __global__ void __launch_bounds__(THREADS, 2) chain_gemm_tma_kernel(const GemmPa
     }
 
     // ---- epilogue ----
-    double* Cg = P.c_dyn ? p.dyn_out : P.C;
-    const double alpha = P.c_dyn ? P.alpha * p.dyn_alpha : P.alpha;
-    const bool atomic = p.split != 0 || P.shared_out != 0;
+    {
+      double* Cg = P.c_dyn ? p.dyn_out : P.C;
+      const double alpha = P.c_dyn ? P.alpha * p.dyn_alpha : P.alpha;
+      const bool atomic = p.split != 0 || P.shared_out != 0;
+      const bool vec_ok = !atomic && !P.accumulate && ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(Cg) & 15) == 0);
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      const int r = warp_m * WM + mt * 8 + g;
-      const int gm = m0 + r;
-      if (r >= BMe || gm >= p.M) continue;
+      for (int mt = 0; mt < MT; ++mt) {
+        const int r = warp_m * WM + mt * 8 + g;
+        const int gm = m0 + r;
+        if (r >= BMe || gm >= p.M) continue;
+        double* crow = Cg + (size_t)gm * p.ldc;
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int c = nt * 8 + 2 * t + e;
-          int gn;
+        for (int nt = 0; nt < NT; ++nt) {
+          // columns 2t, 2t+1 of the 8-wide fragment: same (s) group, consecutive in memory
+          int gn, nvalid;
           if (MODE == TN_NN && d > 1) {
-            const int s = c / BNy, y = n0 + c % BNy;
-            if (s >= d || y >= Ny) continue;
-            gn = s * Ny + y;
+            const int y = n0 + ep_y[nt];
+            gn = ep_s[nt] * Ny + y;
+            nvalid = ep_s[nt] < d ? min(max(Ny - y, 0), 2) : 0;
           } else {
-            gn = n0 + c;
-            if (gn >= p.N) continue;
+            gn = n0 + 0 + nt * 8 + 2 * t;
+            nvalid = min(max(p.N - gn, 0), 2);
           }
-          double* dst = Cg + (size_t)gm * p.ldc + gn;
-          const double v = alpha * acc[mt][nt][e];
-          if (atomic)
-            atomicAdd(dst, v);
-          else if (P.accumulate)
-            *dst += v;
-          else
-            *dst = v;
+          if (nvalid == 0) continue;
+          const double v0 = alpha * acc[mt][nt][0], v1 = alpha * acc[mt][nt][1];
+          double* dst = crow + gn;
+          if (vec_ok && nvalid == 2 && ((gn & 1) == 0)) {
+            *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+          } else if (atomic) {
+            atomicAdd(dst, v0);
+            if (nvalid == 2) atomicAdd(dst + 1, v1);
+          } else if (P.accumulate) {
+            dst[0] += v0;
+            if (nvalid == 2) dst[1] += v1;
+          } else {
+            dst[0] = v0;
+            if (nvalid == 2) dst[1] = v1;
+          }
         }
       }
     }

@@ -162,8 +162,23 @@ extern "C" int tn_effh_plan_create(tn_effh_plan** out_plan, int a, int d, int b,
     // all add into `out` with FP64 atomics: tiles are then visited chunk by chunk, every CTA of the grid works on the same
     // few links at the same time and their operands (Phi_i, XR_i) are shared through L2 instead of being re-read from HBM
     // by every tile (17.9 GB -> ~1.5 GB of DRAM reads per launch at chi = 1024, profiles/r01_ncu_matvec.md).
-    const int kChunk = 3;
+    // The chunk size is chosen so that (chunks x tiles) fills whole waves of the grid: the whole-tile round-robin schedule
+    // then keeps all CTAs inside one chunk; a stream-K split would spread them over all chunks again.
     const int nl = (int)lb.size();
+    int kChunk = 3;
+    {
+      const int BMt = 128, BNt = 64;  // tile of the large configuration
+      const int BMe = d > 1 ? (BMt / d) * d : BMt;
+      const long long tiles = (long long)((a * d + BMe - 1) / BMe) * ((b + BNt - 1) / BNt);
+      const long long G = 2LL * sm_count();
+      double best = -1.0;
+      for (int ch = 4; ch >= 1; --ch) {
+        const long long total = tiles * ((nl + ch - 1) / ch);
+        const double eff = (double)total / (double)(((total + G - 1) / G) * G);
+        if (eff >= 0.93) { kChunk = ch; break; }
+        if (eff > best) { best = eff; kChunk = ch; }
+      }
+    }
     for (int l0 = 0; l0 < nl; l0 += kChunk) {
       ProblemDev q{};
       q.C = nullptr; q.alpha = 1.0; q.link_begin = l0; q.link_count = std::min(kChunk, nl - l0); q.accumulate = 1; q.c_dyn = 1;
