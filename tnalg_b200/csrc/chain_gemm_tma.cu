@@ -6,8 +6,8 @@
 //     in shared memory in the SWIZZLE_128B_ATOM_32B layout: the 32-byte atom `a` of row `r` sits at position a ^ (r & 3)
 //     (measured with tools/microbench/tma_probe.cu), which makes every LDS.64 fragment read conflict-free for both tile
 //     orientations without padding;
-//   * completion is tracked by `full`/`empty` mbarriers per stage: the consumer warps never execute a copy instruction and
-//     never meet at a CTA-wide barrier inside the k loop;
+//   * arrival of a stage is tracked by a `full` mbarrier (complete_tx), its release by a shared-memory arrival counter: the
+//     last consumer warp to finish a stage refills it at once; there is no CTA-wide barrier inside the k loop;
 //   * ragged edges (M, N, K not multiples of the tile) are zero-filled by the TMA unit itself;
 //   * the (s, y) column grouping of the left stage is a 3-D tensor map over psi viewed as (a', s, b): the physical-index
 //     "reshape" is just a coordinate of the box load.
@@ -48,9 +48,6 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   asm volatile(
       "{\n.reg .pred p;\nTN_WAIT_%=:\n"
@@ -79,7 +76,7 @@ __global__ void __launch_bounds__(THREADS, 2) chain_gemm_tma_kernel(const GemmPa
   if (smem_u32(smem) & 1023u) __trap();
   double* const sOpRing = smem + STAGE_ELEMS * STAGES;
   uint64_t* const full = reinterpret_cast<uint64_t*>(sOpRing + kRing * 16);
-  uint64_t* const empty = full + STAGES;
+  int* const done = reinterpret_cast<int*>(full + STAGES);  // per stage: consumer warps that finished reading it
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int warp_m = warp;  // 4 x 1 warps
@@ -91,7 +88,7 @@ __global__ void __launch_bounds__(THREADS, 2) chain_gemm_tma_kernel(const GemmPa
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], THREADS / 32);
+      done[2 * s] = 0;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -182,50 +179,53 @@ __global__ void __launch_bounds__(THREADS, 2) chain_gemm_tma_kernel(const GemmPa
   const CUtensorMap *mapA = nullptr, *mapB = nullptr;
   const LinkDev* Lc = nullptr;
 
-  // ---- producer (thread 0 only): stage one k-block, possibly of a later segment ----
-  auto produce = [&]() {
+  // ---- producer: every thread tracks the cursor of the next k-block to stage (cheap integer state), so that ANY warp can
+  // issue it.  A stage is refilled by the last consumer warp that finishes reading it (shared-memory arrival counter): the
+  // load is issued at the earliest possible moment instead of when one fixed thread happens to come around. ----
+  auto produce = [&](bool issuer) {
     if (!p_valid) return;
     if (ps.left == 0) {
       p_valid = next_segment(ps);
       if (!p_valid) return;
     }
     const int stage = n_fill % STAGES;
-    if (n_fill >= STAGES) mbar_wait(&empty[stage], ((n_fill / STAGES) - 1) & 1);
-    if (ps.link != li_cached) {
-      Lc = p.links + ps.link;
-      mapA = Lc->a_dyn ? &psi_map_a : maps + Lc->a_map;
-      mapB = Lc->b_dyn ? &psi_map_b : maps + Lc->b_map;
-      li_cached = ps.link;
-    }
-    {  // operator of this k-block's link, one ring slot per k-block in flight
-      double* ring = sOpRing + (n_fill % kRing) * 16;
-      const bool hop = (d > 1) && Lc->has_op;
-      ring[15] = hop ? 1.0 : 0.0;
-      if (hop) {
-#pragma unroll
-        for (int i = 0; i < kMaxD * kMaxD; ++i) ring[i] = Lc->op[i];
+    if (issuer) {
+      if (ps.link != li_cached) {
+        Lc = p.links + ps.link;
+        mapA = Lc->a_dyn ? &psi_map_a : maps + Lc->a_map;
+        mapB = Lc->b_dyn ? &psi_map_b : maps + Lc->b_map;
+        li_cached = ps.link;
       }
-    }
-    double* sA = smem + stage * STAGE_ELEMS;
-    double* sB = sA + A_ELEMS;
-    const int k0 = ps.k * BK;
-    mbar_expect_tx(&full[stage], STAGE_BYTES);
+      {  // operator of this k-block's link, one ring slot per k-block in flight
+        double* ring = sOpRing + (n_fill % kRing) * 16;
+        const bool hop = (d > 1) && Lc->has_op;
+        ring[15] = hop ? 1.0 : 0.0;
+        if (hop) {
 #pragma unroll
-    for (int h = 0; h < BK / BOXW; ++h) tma_2d(sA + h * BM * BOXW, mapA, k0 + h * BOXW, ps.m0, &full[stage]);
-    if (MODE == TN_NT) {
+          for (int i = 0; i < kMaxD * kMaxD; ++i) ring[i] = Lc->op[i];
+        }
+      }
+      double* sA = smem + stage * STAGE_ELEMS;
+      double* sB = sA + A_ELEMS;
+      const int k0 = ps.k * BK;
+      mbar_expect_tx(&full[stage], STAGE_BYTES);
 #pragma unroll
-      for (int h = 0; h < BK / BOXW; ++h) tma_2d(sB + h * BN * BOXW, mapB, k0 + h * BOXW, ps.n0, &full[stage]);
-    } else {
-      // B tile: BK k-rows, BN/16 boxes of 16 columns; box q covers tile columns [16q, 16q+16) = one (s, y) group
+      for (int h = 0; h < BK / BOXW; ++h) tma_2d(sA + h * BM * BOXW, mapA, k0 + h * BOXW, ps.m0, &full[stage]);
+      if (MODE == TN_NT) {
 #pragma unroll
-      for (int q = 0; q < BN / BOXW; ++q) {
-        const int c = q * BOXW;
-        const int s = (d > 1) ? c / BNy : 0;
-        const int y = (d > 1) ? c % BNy : c;
-        if (s < d)
-          tma_3d(sB + q * BK * BOXW, mapB, ps.n0 + y, s, k0, &full[stage]);
-        else
-          tma_3d(sB + q * BK * BOXW, mapB, Ny, 0, k0, &full[stage]);  // fully out of range: zero fill, keeps the byte count
+        for (int h = 0; h < BK / BOXW; ++h) tma_2d(sB + h * BN * BOXW, mapB, k0 + h * BOXW, ps.n0, &full[stage]);
+      } else {
+        // B tile: BK k-rows, BN/16 boxes of 16 columns; box q covers tile columns [16q, 16q+16) = one (s, y) group
+#pragma unroll
+        for (int q = 0; q < BN / BOXW; ++q) {
+          const int c = q * BOXW;
+          const int sgrp = (d > 1) ? c / BNy : 0;
+          const int y = (d > 1) ? c % BNy : c;
+          if (sgrp < d)
+            tma_3d(sB + q * BK * BOXW, mapB, ps.n0 + y, sgrp, k0, &full[stage]);
+          else
+            tma_3d(sB + q * BK * BOXW, mapB, Ny, 0, k0, &full[stage]);  // fully out of range: zero fill, keeps the byte count
+        }
       }
     }
     if (++ps.k == p.ipl) {
@@ -236,10 +236,9 @@ __global__ void __launch_bounds__(THREADS, 2) chain_gemm_tma_kernel(const GemmPa
     ++n_fill;
   };
 
-  if (tid == 0) {
+  // the first STAGES k-blocks go into empty stages
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) produce();
-  }
+  for (int s = 0; s < STAGES; ++s) produce(tid == 0);
 
   Segment cs;  // consumer cursor (all threads)
   cs.w = w; cs.prob = 0;
@@ -302,7 +301,6 @@ __global__ void __launch_bounds__(THREADS, 2) chain_gemm_tma_kernel(const GemmPa
     };
 
     for (int jj = 0; jj < n_it; ++jj) {
-      if (tid == 0) produce();  // k-block n_cons + STAGES - 1 of this CTA's work list
       const int stage = n_cons % STAGES;
       mbar_wait(&full[stage], (n_cons / STAGES) & 1);
       const double* sA = smem + stage * STAGE_ELEMS;
@@ -316,8 +314,18 @@ __global__ void __launch_bounds__(THREADS, 2) chain_gemm_tma_kernel(const GemmPa
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) compute_kk(sA, sB, sO, false, kk);
       }
+      // this warp is done with the stage; the last of the THREADS/32 warps refills it with k-block n_cons + STAGES
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[stage]);
+      int last = 0;
+      if (lane == 0) {
+        __threadfence_block();
+        last = (atomicAdd(&done[2 * stage], 1) == THREADS / 32 - 1);
+        if (last) {
+          done[2 * stage] = 0;
+          __threadfence_block();
+        }
+      }
+      produce(last != 0);  // all threads advance the cursor; only the elected lane issues
       ++n_cons;
     }
 
