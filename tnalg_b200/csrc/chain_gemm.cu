@@ -26,9 +26,6 @@ namespace tn {
 
 // tile configuration of the large path; the defaults are the best of the variants measured on B200
 // (profiles/r01_kernel_variants.md): 128x64 CTA tile, BK = 32, 2 stages, two independent CTAs per SM (ping-pong)
-#ifndef TN_STAGES_L
-#define TN_STAGES_L 2
-#endif
 constexpr int BK = kBK;
 constexpr int PAD = 4;
 
@@ -413,15 +410,6 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) chain_gemm_kernel(con
 // ------------------------------------------------------------------------------------------------
 #ifndef TN_CFGL_WN
 #define TN_CFGL_WN 64
-#endif
-#ifndef TN_CFGL_BM
-#define TN_CFGL_BM 128
-#endif
-#ifndef TN_CFGL_BN
-#define TN_CFGL_BN 64
-#endif
-#ifndef TN_CFGL_CTAS
-#define TN_CFGL_CTAS 2
 #endif
 using CfgL = TileCfg<TN_CFGL_BM, TN_CFGL_BN, 32, TN_CFGL_WN, TN_STAGES_L, TN_CFGL_CTAS>;  // default: 4 warps of 32x64, 64 accumulator doubles per thread
 using CfgS = TileCfg<64, 64, 32, 32, (TN_BK > 16 ? 3 : 4)>;    // 128 threads, 32 accumulator doubles per thread

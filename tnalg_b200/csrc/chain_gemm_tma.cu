@@ -26,9 +26,11 @@ namespace tn {
 
 namespace {
 #ifndef TN_TMA_STAGES
-#define TN_TMA_STAGES 2
+#define TN_TMA_STAGES TN_STAGES_L
 #endif
-constexpr int BM = 128, BN = 64, BK = kBK, WM = 32, WN = 64, STAGES = TN_TMA_STAGES, THREADS = 128;
+constexpr int BM = kTileBM, BN = kTileBN, BK = kBK, WM = 32, WN = 64, STAGES = TN_TMA_STAGES;
+constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN, THREADS = WARPS_M * WARPS_N * 32;
+static_assert(BM == 128 && BN % WN == 0, "TMA kernel: unsupported tile");
 constexpr int MT = WM / 8, NT = WN / 8;
 constexpr int BOXW = 16;                      // doubles per box row (128 bytes)
 constexpr int A_ELEMS = BM * BK;              // two boxes of BM x 16
@@ -69,7 +71,7 @@ __device__ __forceinline__ void tma_3d(void* dst, const CUtensorMap* map, int c0
 // psi_map_a: psi as the (M = a*d) x (K = b) A operand of the right stage (2-D, box 16 x BM)
 // psi_map_b: psi as the (K = a') x (s) x (y = b) B operand of the left stage (3-D, box 16 x 1 x BK)
 template <int MODE>
-__global__ void __launch_bounds__(THREADS, 2) chain_gemm_tma_kernel(const GemmParams p, const CUtensorMap* __restrict__ maps,
+__global__ void __launch_bounds__(THREADS, kTileCtas) chain_gemm_tma_kernel(const GemmParams p, const CUtensorMap* __restrict__ maps,
                                                                     const __grid_constant__ CUtensorMap psi_map_a,
                                                                     const __grid_constant__ CUtensorMap psi_map_b) {
   extern __shared__ __align__(1024) double smem[];  // the swizzle pattern is a function of the shared address: 1024-byte aligned base
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(THREADS, 2) chain_gemm_tma_kernel(const GemmPa
   int* const done = reinterpret_cast<int*>(full + STAGES);  // per stage: consumer warps that finished reading it
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int warp_m = warp;  // 4 x 1 warps
+  const int warp_m = warp % WARPS_M, warp_n = warp / WARPS_M;
   const int d = p.d;
   const int BNy = (MODE == TN_NN && d > 1) ? ((BN / d) / BOXW) * BOXW : BN;  // y values per tile (multiple of the box width)
   const int BMe = (MODE == TN_NT && d > 1) ? (BM / d) * d : BM;
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(THREADS, 2) chain_gemm_tma_kernel(const GemmPa
   int n_s[NT], n_y[NT];
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
-    const int c = nt * 8 + g;
+    const int c = warp_n * WN + nt * 8 + g;
     const int s = (MODE == TN_NN && d > 1) ? c / BNy : 0;
     n_y[nt] = (MODE == TN_NN && d > 1) ? c % BNy : c;
     n_s[nt] = s < d ? s : 0;
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(THREADS, 2) chain_gemm_tma_kernel(const GemmPa
   int ep_s[NT], ep_y[NT];  // epilogue: (s, y offset) of fragment columns 2t, 2t+1 of each n-tile (NN with an operator grouping)
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
-    const int c = 0 + nt * 8 + 2 * t;
+    const int c = warp_n * WN + nt * 8 + 2 * t;
     ep_s[nt] = (MODE == TN_NN && d > 1) ? c / BNy : 0;
     ep_y[nt] = (MODE == TN_NN && d > 1) ? c % BNy : c;
   }
@@ -275,7 +277,7 @@ __global__ void __launch_bounds__(THREADS, 2) chain_gemm_tma_kernel(const GemmPa
       }
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        const int c = nt * 8 + g;
+        const int c = warp_n * WN + nt * 8 + g;
         if (MODE == TN_NT) {
           b[nt] = sB[h * (BN * BOXW) + c * BOXW + ((atom ^ (g & 3)) << 2) + t];
         } else {
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(THREADS, 2) chain_gemm_tma_kernel(const GemmPa
             gn = ep_s[nt] * Ny + y;
             nvalid = ep_s[nt] < d ? min(max(Ny - y, 0), 2) : 0;
           } else {
-            gn = n0 + 0 + nt * 8 + 2 * t;
+            gn = n0 + warp_n * WN + nt * 8 + 2 * t;
             nvalid = min(max(p.N - gn, 0), 2);
           }
           if (nvalid == 0) continue;

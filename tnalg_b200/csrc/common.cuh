@@ -71,6 +71,20 @@ struct Carver {
 #define TN_BK 32
 #endif
 constexpr int kBK = TN_BK;
+// CTA tile of the large configuration (both staging paths): 128x64 with two CTAs per SM by default
+#ifndef TN_CFGL_BM
+#define TN_CFGL_BM 128
+#endif
+#ifndef TN_CFGL_BN
+#define TN_CFGL_BN 64
+#endif
+#ifndef TN_CFGL_CTAS
+#define TN_CFGL_CTAS 2
+#endif
+#ifndef TN_STAGES_L
+#define TN_STAGES_L 2
+#endif
+constexpr int kTileBM = TN_CFGL_BM, kTileBN = TN_CFGL_BN, kTileCtas = TN_CFGL_CTAS;
 
 // ---- device-side descriptors of the chain GEMM (built by the host wrappers in chain_gemm.cu) ----
 constexpr int kMaxD = TN_MAX_PHYS_DIM;

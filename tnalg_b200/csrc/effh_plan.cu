@@ -167,10 +167,10 @@ extern "C" int tn_effh_plan_create(tn_effh_plan** out_plan, int a, int d, int b,
     const int nl = (int)lb.size();
     int kChunk = 3;
     {
-      const int BMt = 128, BNt = 64;  // tile of the large configuration
+      const int BMt = kTileBM, BNt = kTileBN;  // tile of the large configuration
       const int BMe = d > 1 ? (BMt / d) * d : BMt;
       const long long tiles = (long long)((a * d + BMe - 1) / BMe) * ((b + BNt - 1) / BNt);
-      const long long G = 2LL * sm_count();
+      const long long G = (long long)kTileCtas * sm_count();
       double best = -1.0;
       for (int ch = 4; ch >= 1; --ch) {
         const long long total = tiles * ((nl + ch - 1) / ch);
