@@ -234,9 +234,15 @@ def test_matvec_without_any_block(be):
 @pytest.mark.parametrize('shape,counts', [((1, 2, 2), (0, 3, 0)), ((2, 2, 4), (3, 3, 1)), ((8, 2, 8), (3, 3, 2)), ((24, 2, 24), (3, 3, 4)),
                                           ((40, 2, 40), (3, 3, 3))])
 @pytest.mark.parametrize('tol', [1e-5, 1e-12])
-def test_lanczos_vs_dense_eigh(be, shape, counts, tol):
-    """dominant eigenpair of 1 - tau*H_eff: eigenvalue, residual and (for tight tol) the eigenvector itself"""
+@pytest.mark.parametrize('fused', [True, False])
+def test_lanczos_vs_dense_eigh(be, shape, counts, tol, fused, monkeypatch):
+    """dominant eigenpair of 1 - tau*H_eff: eigenvalue, residual and (for tight tol) the eigenvector itself; both the fused
+    cooperative re-orthogonalisation kernel (small vectors) and the streaming kernels with the DGKS-conditional second pass"""
     from tests.cpu_backend import CpuPlan
+    if fused:
+        monkeypatch.delenv('TNALG_NO_FUSED_ORTH', raising=False)
+    else:
+        monkeypatch.setenv('TNALG_NO_FUSED_ORTH', '1')
     rng = np.random.RandomState(11 + sum(shape))
     a, d, b = shape
     g = random_groups(rng, a, d, b, *counts)

@@ -25,10 +25,11 @@ long long plan_dim(const tn_effh_plan* P);
 struct LanczosState {
   double alpha[kMaxNcv];
   double beta[kMaxNcv];   // beta[j] couples v_j and v_{j+1}
-  double h[kMaxNcv + 1];  // CGS pass 1 coefficients
+  double h[kMaxNcv + 2];  // CGS pass 1 coefficients; h[j+1] = w.w of step j (DGKS test)
   double h2[kMaxNcv + 1]; // CGS pass 2 coefficients
   double u[kMaxNcv];      // Ritz vector in the Krylov basis
   double nrm2, inv_beta;
+  int need2, pad2;        // DGKS: second Gram-Schmidt pass needed for the current step
   // status record copied to the host once per cycle
   double theta, resid, lambda, s_restart;
   int converged, breakdown, m_eff, ql_fail;
@@ -42,6 +43,18 @@ __global__ void lanczos_init_kernel(LanczosState* st) {
   st->inv_beta = 0.0;
   const double n2 = st->nrm2;
   st->inv_beta = n2 > 0.0 ? 1.0 / sqrt(n2) : 0.0;
+}
+
+// DGKS test after the first Gram-Schmidt pass of step j: |w'|^2 = |w|^2 - sum h_i^2 (Pythagoras); a second pass is needed
+// only when the first one removed more than half of |w|^2 (ARPACK applies the same test)
+__global__ void lanczos_dgks_kernel(LanczosState* st, int j) {
+  const double ww = st->h[j + 1];
+  double s = 0.0;
+  for (int i = 0; i <= j; ++i) s += st->h[i] * st->h[i];
+  const int need = !((ww - s) > 0.5 * ww);
+  st->need2 = need;
+  if (!need)
+    for (int i = 0; i <= j; ++i) st->h2[i] = 0.0;
 }
 
 // after the two CGS passes and the norm of step j
@@ -263,7 +276,7 @@ extern "C" size_t tn_lanczos_workspace_bytes(long long n, int ncv) {
   const long long m = std::min<long long>(std::max(ncv, 2), std::min<long long>(n, kMaxNcv));
   const size_t ldv = (size_t)((n + 1) / 2 * 2);
   return align_up(sizeof(double) * ldv * (size_t)(m + 2)) +
-         align_up(sizeof(double) * std::max<size_t>((size_t)(m + 1) * dot_chunks(n), (size_t)3 * 2048 * (kMaxNcv + 1))) +
+         align_up(sizeof(double) * std::max<size_t>((size_t)(m + 2) * dot_chunks(n), (size_t)3 * 2048 * (kMaxNcv + 1))) +
          align_up(sizeof(LanczosState)) + align_up(sizeof(unsigned)) + 1024;
 }
 
@@ -284,7 +297,7 @@ extern "C" int tn_lanczos_lm1(tn_effh_plan* plan, double tau, const double* v0, 
   const long long ldv = (n + 1) / 2 * 2;
   Carver cw(workspace, workspace_bytes);
   double* V = cw.take<double>((size_t)ldv * (m + 2));
-  double* partial = cw.take<double>(std::max<size_t>((size_t)(m + 1) * dot_chunks(n), (size_t)3 * 2048 * (kMaxNcv + 1)));
+  double* partial = cw.take<double>(std::max<size_t>((size_t)(m + 2) * dot_chunks(n), (size_t)3 * 2048 * (kMaxNcv + 1)));
   LanczosState* st = cw.take<LanczosState>(1);
   unsigned* counter = cw.take<unsigned>(1);
   TN_REQUIRE(V && partial && st && counter, "tn_lanczos_lm1: workspace carve failed");
@@ -347,10 +360,13 @@ extern "C" int tn_lanczos_lm1(tn_effh_plan* plan, double tau, const double* v0, 
         TN_LAUNCHED();
       } else {
         // streaming path (HBM-bound kernels): CGS2 against v_0..v_j, norm, bookkeeping, scale
-        TN_CHECK(launch_multidot(V, ldv, j + 1, w, n, st->h, partial, counter, stream));
+        // pass 1 also yields w.w (w = v_{j+1} is the vector after v_j in the workspace) for the DGKS test
+        TN_CHECK(launch_multidot(V, ldv, j + 2, w, n, st->h, partial, counter, stream));
+        lanczos_dgks_kernel<<<1, 1, 0, stream>>>(st, j);
+        TN_LAUNCHED();
         TN_CHECK(launch_multi_axpy(w, V, ldv, j + 1, st->h, n, stream));
-        TN_CHECK(launch_multidot(V, ldv, j + 1, w, n, st->h2, partial, counter, stream));
-        TN_CHECK(launch_multi_axpy(w, V, ldv, j + 1, st->h2, n, stream));
+        TN_CHECK(launch_multidot(V, ldv, j + 1, w, n, st->h2, partial, counter, stream, &st->need2));
+        TN_CHECK(launch_multi_axpy(w, V, ldv, j + 1, st->h2, n, stream, &st->need2));
         TN_CHECK(launch_multidot(w, ldv, 1, w, n, &st->nrm2, partial, counter, stream));
         lanczos_finish_step_kernel<<<1, 1, 0, stream>>>(st, j);
         TN_LAUNCHED();

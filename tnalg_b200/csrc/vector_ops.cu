@@ -66,7 +66,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 // (atomic ticket) sums the per-chunk partials in index order, so the result is bit-reproducible.
 __global__ void __launch_bounds__(kDotThreads) multidot_kernel(const double* __restrict__ V, long long ldv, const double* __restrict__ w,
                                                                long long n, double* __restrict__ result,
-                                                               double* __restrict__ partial, unsigned* counter) {
+                                                               double* __restrict__ partial, unsigned* counter, const int* skip_flag) {
+  if (skip_flag && *skip_flag == 0) return;  // uniform over the grid
   const int chunk = blockIdx.x, vec = blockIdx.y, chunks = gridDim.x;
   const double* v = V + (long long)vec * ldv;
   const long long e0 = (long long)chunk * kDotChunk;
@@ -101,15 +102,16 @@ __global__ void __launch_bounds__(kDotThreads) multidot_kernel(const double* __r
 }
 
 int launch_multidot(const double* V, long long ldv, int nvec, const double* w, long long n, double* result, double* partial,
-                    unsigned* counter, cudaStream_t stream) {
+                    unsigned* counter, cudaStream_t stream, const int* skip_flag) {
   dim3 grid(dot_chunks(n), nvec);
-  multidot_kernel<<<grid, kDotThreads, 0, stream>>>(V, ldv, w, n, result, partial, counter);
+  multidot_kernel<<<grid, kDotThreads, 0, stream>>>(V, ldv, w, n, result, partial, counter, skip_flag);
   TN_LAUNCHED();
   return TN_OK;
 }
 
 __global__ void multi_axpy_kernel(double* __restrict__ w, const double* __restrict__ V, long long ldv, int nvec,
-                                  const double* __restrict__ h, long long n) {
+                                  const double* __restrict__ h, long long n, const int* skip_flag) {
+  if (skip_flag && *skip_flag == 0) return;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
     double v = w[e];
     for (int i = 0; i < nvec; ++i) v -= h[i] * V[(long long)i * ldv + e];
@@ -117,9 +119,10 @@ __global__ void multi_axpy_kernel(double* __restrict__ w, const double* __restri
   }
 }
 
-int launch_multi_axpy(double* w, const double* V, long long ldv, int nvec, const double* h, long long n, cudaStream_t stream) {
+int launch_multi_axpy(double* w, const double* V, long long ldv, int nvec, const double* h, long long n, cudaStream_t stream,
+                      const int* skip_flag) {
   int grid = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8);
-  multi_axpy_kernel<<<grid, 256, 0, stream>>>(w, V, ldv, nvec, h, n);
+  multi_axpy_kernel<<<grid, 256, 0, stream>>>(w, V, ldv, nvec, h, n, skip_flag);
   TN_LAUNCHED();
   return TN_OK;
 }

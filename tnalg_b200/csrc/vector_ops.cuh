@@ -16,10 +16,12 @@ int launch_site_op_axpby(double* out, const double* x, long long a, int d, long 
 // counter: one unsigned zero-initialised once (the kernel resets it).  Optional fused bookkeeping is done by callers
 // in a follow-up single-thread kernel.
 int dot_chunks(long long n);
+// skip_flag (device int, may be null): when *skip_flag == 0 the kernel returns at once (conditional second CGS pass)
 int launch_multidot(const double* V, long long ldv, int nvec, const double* w, long long n, double* result, double* partial,
-                    unsigned* counter, cudaStream_t stream);
+                    unsigned* counter, cudaStream_t stream, const int* skip_flag = nullptr);
 // w[e] -= sum_i h[i] * V[i*ldv + e]
-int launch_multi_axpy(double* w, const double* V, long long ldv, int nvec, const double* h, long long n, cudaStream_t stream);
+int launch_multi_axpy(double* w, const double* V, long long ldv, int nvec, const double* h, long long n, cudaStream_t stream,
+                      const int* skip_flag = nullptr);
 // y[e] = sum_i u[i] * V[i*ldv + e]
 int launch_combine(double* y, const double* V, long long ldv, int nvec, const double* u, long long n, cudaStream_t stream);
 // x[e] *= *scale (device scalar)
