@@ -478,6 +478,32 @@ class OracleMps:
         return float(np.linalg.norm(self.mps[self.center]))
 
 
+def truncate_mps(mps, chi):
+    """library/MPSClass.py:186-247 with is_trun=True (as driven by truncate_virtual_bonds :909-923, way != 'simple'):
+    centre at site 0, then an SVD sweep 0 -> L-1 that keeps the chi largest singular triplets of every bond and normalises
+    the tensor absorbing the remainder.  Returns (tensors with the centre at L-1, kept singular values per bond)."""
+    A = OracleMps(len(mps), mps[0].shape[1], max(t.shape[2] for t in mps), None, way='qr', mps=mps)
+    A.correct_orthogonal_center(0)
+    out, lms = [np.array(t) for t in A.mps], []
+    for n in range(len(out) - 1):
+        a, d, b = out[n].shape
+        u, lm, vh = np.linalg.svd(out[n].reshape(a * d, b), full_matrices=False)
+        k = min(chi, lm.size)
+        out[n] = u[:, :k].reshape(a, d, k)
+        out[n + 1] = np.einsum('kb,bsc->ksc', lm[:k, None] * vh[:k], out[n + 1])
+        out[n + 1] /= np.linalg.norm(out[n + 1])
+        lms.append(lm[:k])
+    return out, lms
+
+
+def mps_overlap(x, y):
+    """<x|y> of two open-boundary MPS (lists of (a,d,b) tensors)"""
+    e = np.ones((1, 1))
+    for tx, ty in zip(x, y):
+        e = np.einsum('ab,asc,bsd->cd', e, tx.conj(), ty)
+    return e[0, 0]
+
+
 def bond_energies(eb_full, positions, index2):
     """sum the per-term energies onto their bond (get_bond_energies, DMRG_anyH.py:250-258)."""
     eb = np.zeros((positions.shape[0], 1))

@@ -14,6 +14,7 @@ Cases
                    set, transfers, QR/SVD gauge moves, observables
   pr_fixtures      numbers extracted from the reference's own data_dmrg/*.pr result pickles
   docstring_kats   integer known-answer vectors printed in TensorBasicModule.py docstrings
+  truncation_lib   library/ generation: truncate_virtual_bonds(chi=5) of a random chi=12 MPS (kept spectrum, tensors)
 """
 import os
 import pickle
@@ -191,6 +192,30 @@ def docstring_kats():
                 r2l_id=tm.bound_vec_operator_right2left(T3), r2l_v=tm.bound_vec_operator_right2left(T3, v=v))
 
 
+def truncation_case():
+    """a12: the library/ generation's SVD truncation of every bond (library/MPSClass.py:186-247, 909-923), run from the
+    package-style tree (library.MPSClass); needs a stub for matplotlib.cm on top of the shim."""
+    import importlib
+    import types
+    if 'matplotlib.cm' not in sys.modules:
+        sys.modules['matplotlib.cm'] = types.ModuleType('matplotlib.cm')
+        sys.modules['matplotlib'].cm = sys.modules['matplotlib.cm']
+    lib = importlib.import_module('library.MPSClass')
+    np.random.seed(3)
+    A = lib.MpsOpenBoundaryClass(8, 2, 12, way='qr', ini_way='r')
+    out = {'chi1': 5, 'center': 7, 'l': 8, 'd': 2, 'chi0': 12}
+    for n, t in enumerate(A.mps):
+        out['mps_in_%d' % n] = t.copy()
+    A.correct_orthogonal_center(0)
+    A.truncate_virtual_bonds(5, center=7, way='full')
+    for n, t in enumerate(A.mps):
+        out['mps_out_%d' % n] = t.copy()
+    for n, lm in enumerate(A.lm):
+        out['lm_%d' % n] = lm.copy()
+    out['virtual_dim'] = np.asarray(A.virtual_dim)
+    return out
+
+
 def main():
     cases = {
         'e2e_chain12': lambda: pack_run(chain_para(l=12, chi=16, **TIGHT), 0),
@@ -199,6 +224,7 @@ def main():
         'percall_j1j2': percall_case,
         'pr_fixtures': pr_fixtures,
         'docstring_kats': docstring_kats,
+        'truncation_lib': truncation_case,
     }
     for name, fn in cases.items():
         data = fn()

@@ -131,3 +131,9 @@ def test_observables_of_reference_result_pickles(golden, tag):
         ref = g['%s_lm_%d' % (tag, n)]
         assert np.abs(A.lm[n] - ref).max() <= 1e-10 * ref.max() + 1e-13, n
     assert np.abs(A.ent.reshape(-1) - g[tag + '_ent'].reshape(-1)).max() < 1e-9
+
+
+def test_truncate_virtual_bonds_vs_oracle():
+    """a12 on the device: Jacobi SVD with k_keep as the truncating gauge move"""
+    from tests.test_host_logic_cpu import _check_truncation
+    _check_truncation()

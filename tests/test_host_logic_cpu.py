@@ -194,3 +194,46 @@ def test_observables_of_reference_result_pickles(golden, cpu_be, tag):
     for n in range(L - 1):
         ref = g['%s_lm_%d' % (tag, n)]
         assert np.abs(A.lm[n] - ref).max() <= 1e-10 * ref.max() + 1e-13, n
+
+
+def test_truncate_virtual_bonds_vs_oracle(cpu_be):
+    """a12: SVD truncation of every bond to chi (library/MPSClass.py:186-247, 909-923)"""
+    _check_truncation()
+
+
+def _check_truncation():
+    import os
+    from oracle import dmrg_oracle as orc
+    from tnalg_b200.MPSClass import MpsOpenBoundaryClass
+    # against the reference's library/ generation (golden) ...
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'truncation_lib.npz')))
+    Lg = int(g['l'])
+    G = MpsOpenBoundaryClass(Lg, int(g['d']), int(g['chi0']))
+    G.load_tensors([g['mps_in_%d' % n] for n in range(Lg)], center=0)
+    G.center = -1
+    G.correct_orthogonal_center(0)
+    G.truncate_virtual_bonds(int(g['chi1']), center=int(g['center']))
+    assert np.array_equal(G.virtual_dim, g['virtual_dim'])
+    for n in range(Lg - 1):
+        assert np.abs(G.lm[n] - g['lm_%d' % n]).max() <= 1e-10 * g['lm_%d' % n].max(), n
+    outg = [np.array(t.cpu().numpy()) for t in G.mps]
+    assert abs(abs(orc.mps_overlap([g['mps_out_%d' % n] for n in range(Lg)], outg)) - 1) < 1e-10
+    # ... and against the oracle on a fresh random state
+    np.random.seed(3)
+    L, d, chi0, chi1 = 8, 2, 12, 5
+    A = MpsOpenBoundaryClass(L, d, chi0)
+    host = [np.array(t.cpu().numpy()) for t in A.mps]
+    ref, lms = orc.truncate_mps(host, chi1)
+    A.correct_orthogonal_center(0)
+    A.truncate_virtual_bonds(chi1, center=L - 1)
+    got = [np.array(t.cpu().numpy()) for t in A.mps]
+    assert max(A.virtual_dim) == chi1 and [t.shape for t in got] == [t.shape for t in ref]
+    for n in range(L - 1):
+        assert np.abs(A.lm[n] - lms[n]).max() <= 1e-10 * lms[n].max()           # kept spectrum
+    assert abs(abs(orc.mps_overlap(ref, got)) - 1) < 1e-10                       # same state up to gauge/sign
+    assert abs(A.norm_mps() - 1) < 1e-12
+    # 'simple' way: plain index cut + re-orthogonalisation
+    B = MpsOpenBoundaryClass(L, d, chi0)
+    B.correct_orthogonal_center(0)
+    B.truncate_virtual_bonds(chi1, center=3, way='simple')
+    assert max(B.virtual_dim) <= chi1 and B.center == 3 and abs(B.norm_mps() - 1) < 1e-12

@@ -147,3 +147,15 @@ def test_dense_ed_cross_check():
     ob, A, info = orc.dmrg_finite_size(para, seed=5)
     e0 = np.linalg.eigvalsh(orc.dense_hamiltonian(para))[0]
     assert abs(ob['e_per_site'][0] * para['l'] - e0) < 1e-10
+
+
+def test_truncation_against_library_generation(golden):
+    """a12 oracle pinned against the reference's library/ generation (library/MPSClass.py:186-247, 909-923)"""
+    g = golden('truncation_lib')
+    L = int(g['l'])
+    ref, lms = orc.truncate_mps([g['mps_in_%d' % n] for n in range(L)], int(g['chi1']))
+    out = [g['mps_out_%d' % n] for n in range(L)]
+    assert [t.shape for t in ref] == [t.shape for t in out]
+    for n in range(L - 1):
+        assert np.abs(lms[n] - g['lm_%d' % n]).max() <= 1e-12 * g['lm_%d' % n].max()
+    assert abs(abs(orc.mps_overlap(ref, out)) - 1) < 1e-12

@@ -196,31 +196,61 @@ class MpsOpenBoundaryClass(MpsBasic):
             Qt = Q.t().contiguous().reshape(k, d, b)
         return Qt, R, k, lm
 
-    def orthogonalize_mps(self, l0, l1):
+    def orthogonalize_mps(self, l0, l1, normalize=False, is_trun=False, chi=-1):
+        """gauge moves from l0 to l1 (MPSClass.py:143-167).  The extra arguments are those of the library generation
+        (library/MPSClass.py:186-247): with is_trun the decomposition is an SVD and the new bond keeps the chi largest
+        singular triplets (tn_svd_jacobi with k_keep); normalize rescales the tensor that absorbed the remainder."""
         self._ensure_device()
         be = self._be
-        if l0 < l1:
-            for n in range(l0, l1):
-                Q, R, dim, lm = self._decompose(n, True)
-                self.virtual_dim[n + 1] = dim
+        way0 = self.decomp_way
+        if is_trun:
+            self.decomp_way = 'svd'
+        try:
+            step = 1 if l0 < l1 else -1
+            for n in range(l0, l1, step):
+                Q, R, dim, lm = self._decompose(n, step == 1)
+                if is_trun and dim > chi > 0:
+                    # keep the leading chi triplets: Q columns / rows and the matching rows of R = diag(lm) Vt
+                    Q = Q[:, :, :chi].contiguous() if step == 1 else Q[:chi].contiguous()
+                    R = R[:chi].contiguous()
+                    lm = lm[:chi]
+                    dim = chi
+                bond = n + 1 if step == 1 else n
+                self.virtual_dim[bond] = dim
                 if lm.size > 0 and self.center > -1:
-                    self.lm[n] = lm.copy()
+                    self.lm[bond - 1] = lm.copy()
                 self.mps[n] = Q
-                # absorb_matrix2tensor(mps[n+1], R^T, 0): new[k,s,b] = sum_j R[k,j] T[j,s,b]
-                self.mps[n + 1] = be.mode_product(self.mps[n + 1], R.t().contiguous(), 0)
-            self.orthogonality[l0:l1] = -1
-            self.orthogonality[l1] = 0
-        elif l0 > l1:
-            for n in range(l0, l1, -1):
-                Q, R, dim, lm = self._decompose(n, False)
-                self.virtual_dim[n] = dim
-                if lm.size > 0 and self.center > -1:
-                    self.lm[n - 1] = lm.copy()
-                self.mps[n] = Q
-                # absorb_matrix2tensor(mps[n-1], R^T, 2): new[a,s,k] = sum_j T[a,s,j] R[k,j]
-                self.mps[n - 1] = be.mode_product(self.mps[n - 1], R.t().contiguous(), 2)
-            self.orthogonality[l0:l1:-1] = 1
-            self.orthogonality[l1] = 0
+                # absorb_matrix2tensor(neighbour, R^T, 0 or 2)
+                self.mps[n + step] = be.mode_product(self.mps[n + step], R.t().contiguous(), 0 if step == 1 else 2)
+                if normalize:
+                    self.mps[n + step] = self.mps[n + step] / be.norm(self.mps[n + step])
+            if l0 < l1:
+                self.orthogonality[l0:l1] = -1
+                self.orthogonality[l1] = 0
+            elif l0 > l1:
+                self.orthogonality[l0:l1:-1] = 1
+                self.orthogonality[l1] = 0
+        finally:
+            self.decomp_way = way0
+
+    def truncate_virtual_bonds(self, chi1, center, way='full'):
+        """reduce every bond to at most chi1 (library/MPSClass.py:909-923).  way='full': SVD-truncating sweep from site 0 to
+        L-1 (optimal bond by bond); way='simple': cut the index ranges and re-orthogonalise."""
+        self._ensure_device()
+        if way == 'simple':
+            for n in range(self.length):
+                t = self.mps[n]
+                self.mps[n] = t[:min(t.shape[0], chi1), :, :min(t.shape[2], chi1)].contiguous()
+            self.virtual_dim = np.array([self.mps[0].shape[0]] + [t.shape[2] for t in self.mps])
+            self.center = -1
+            self.central_orthogonalization(center)
+            self.mps[center] = self.mps[center] / self._be.norm(self.mps[center])
+        else:
+            self.correct_orthogonal_center(0)
+            self.orthogonalize_mps(0, self.length - 1, normalize=True, is_trun=True, chi=chi1)
+            self.center = self.length - 1
+            if center != self.length - 1:
+                self.correct_orthogonal_center(center)
 
     def central_orthogonalization(self, lc, l0=0, l1=-1):
         if l1 == -1:
