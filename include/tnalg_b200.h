@@ -173,7 +173,9 @@ int tn_lanczos_lm1(tn_effh_plan* plan, double tau, const double* v0 /* [dev] n *
  * One-sided Jacobi SVD (a7 'svd' branch, a11, a12): A (m,n) row-major = U diag(S) Vt, singular values sorted
  * in decreasing order, k = min(m,n) triplets of which the first k_keep are written (truncation to chi,
  * library/MPSClass.py:186-247,1676-1686).  U is (m,k_keep), S (k_keep), Vt (k_keep,n); U or Vt may be NULL.
- * Blocking.  sweeps_out [host] receives the number of Jacobi sweeps.
+ * Blocking.  sweeps_out [host] receives the number of Jacobi sweeps.  Callers should pass the transposed triangular factor
+ * of a QR factorisation (Drmac-Veselic preconditioning, tnalg_b200/ops.py:svd): ~8 sweeps and high relative accuracy of the
+ * small singular values, versus 20-50 sweeps on a raw ill-conditioned matrix.
  * -------------------------------------------------------------------------------------------------- */
 size_t tn_svd_workspace_bytes(int m, int n);
 int tn_svd_jacobi(const double* A /* [dev] */, int m, int n, int k_keep, double* U /* [dev] */, double* S /* [dev] */,

@@ -297,6 +297,23 @@ def test_svd_jacobi_vs_lapack(be, shape):
         assert np.abs((U2 * S2) @ Vt2 - (U[:, :kk] * S[:kk]) @ Vt[:kk]).max() < 1e-12
 
 
+def test_svd_ill_conditioned_preconditioned(be):
+    """generic matrix with singular values over ten decades: QR-preconditioned Jacobi converges in a few sweeps and keeps
+    every singular value to high relative accuracy (the raw kernel needs many more sweeps)"""
+    rng = np.random.RandomState(2)
+    m, n = 384, 192
+    s = np.logspace(0, -10, n)
+    A = (np.linalg.qr(rng.randn(m, n))[0] * s) @ np.linalg.qr(rng.randn(n, n))[0].T
+    U, S, Vt = [be.to_numpy(x) for x in be.svd(be.from_numpy(A))]
+    assert be.last_svd_sweeps <= 14
+    assert np.abs(S / s - 1).max() < 1e-5          # A itself carries ~1e-16 absolute noise: 1e-6 relative at 1e-10
+    assert np.abs(S[:n // 2] / s[:n // 2] - 1).max() < 1e-10
+    assert np.abs(U.T @ U - np.eye(n)).max() < 1e-12 and np.abs(Vt @ Vt.T - np.eye(n)).max() < 1e-12
+    assert np.abs((U * S) @ Vt - A).max() < 1e-13
+    U0, S0, Vt0 = [be.to_numpy(x) for x in be.svd(be.from_numpy(A), precondition=False)]
+    assert np.abs(S0 - s).max() < 1e-10 and be.last_svd_sweeps > 14
+
+
 def test_svd_matches_cusolver_baseline(be):
     """cuSOLVER (torch.linalg.svd) is kept only as a checked baseline (north_star)"""
     import torch

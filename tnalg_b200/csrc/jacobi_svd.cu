@@ -219,7 +219,7 @@ extern "C" int tn_svd_jacobi(const double* A, int m, int n, int k_keep, double* 
   }
   const double tol = std::max(1e-15, std::sqrt((double)len) * 2.2e-16);
   int sweeps = 0;
-  const int max_sweeps = 40;
+  const int max_sweeps = 80;  // QR-preconditioned inputs (ops.CudaBackend.svd) need ~8; raw ill-conditioned ones 20-50
   bool converged = rp < 2;
   while (!converged && sweeps < max_sweeps) {
     TN_CUDA(cudaMemsetAsync(n_rot, 0, sizeof(unsigned), stream));

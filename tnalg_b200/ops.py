@@ -251,8 +251,29 @@ class CudaBackend:
         return lam.value, out, nmv.value, resid.value, st == 0
 
     # ---- a7/a11/a12: factorizations ----
-    def svd(self, A, k_keep=None):
-        """A (m,n) -> U (m,k), S (k), Vt (k,n) with the k largest singular triplets (one-sided Jacobi)."""
+    def svd(self, A, k_keep=None, precondition=True):
+        """A (m,n) -> U (m,k), S (k), Vt (k,n) with the k largest singular triplets.
+        One-sided Jacobi (tn_svd_jacobi) on R^T of a QR factorisation of A (Drmac-Veselic preconditioning): the
+        triangular factor makes Jacobi converge in ~8 sweeps instead of 20-40 on ill-conditioned inputs and keeps the
+        small Schmidt values accurate to high relative precision; U = Q . U_R is one chain-GEMM call."""
+        A = A.contiguous()
+        m, n = A.shape
+        k = min(m, n) if k_keep is None else min(k_keep, m, n)
+        if m < n:  # work on the transpose: A^T = U' S V'^T  =>  A = V' S U'^T
+            U2, S, Vt2 = self.svd(A.t().contiguous(), k_keep=k, precondition=precondition)
+            return Vt2.t().contiguous(), S, U2.t().contiguous()
+        if precondition and n > 1:
+            Q, R = self.qr(A)                               # (m,n), (n,n)
+            Ux, S, Vtx = self._jacobi(R.t().contiguous())   # R^T = Ux S Vtx  =>  A = (Q Vtx^T) S Ux^T
+            U = self.empty(m, n)
+            self._gemm(1, m, n, n, Q.contiguous(), Vtx, n, n, U)   # U[i,j] = sum_l Q[i,l] Vtx[j,l]   (NT)
+            Vt = Ux.t().contiguous()
+            if k < n:
+                U, S, Vt = U[:, :k].contiguous(), S[:k].contiguous(), Vt[:k].contiguous()
+            return U, S, Vt
+        return self._jacobi(A, k)
+
+    def _jacobi(self, A, k_keep=None):
         A = A.contiguous()
         m, n = A.shape
         k = min(m, n) if k_keep is None else min(k_keep, m, n)
