@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TN_MAX_PHYS_DIM 3 /* d = 2 (spin-1/2) and d = 3 (spin-1), Parameters.py:440-446 */
+#define TN_MAX_PHYS_DIM 4 /* d = 2 (spin-1/2), d = 3 (spin-1, Parameters.py:440-446), d = 4 (two spin-1/2 sites of the two-site update) */
 
 typedef enum {
   TN_OK = 0,

@@ -579,8 +579,72 @@ def dense_hamiltonian(para):
     for n in range(para['index1'].shape[0]):
         o = np.real(ops[int(para['index1'][n, 1])])
         if np.linalg.norm(o) > 0:
-            h += float(para['coeff1'][n]) * site_op(o, int(para['index1'][n, 0]))
+            h += float(np.ravel(para['coeff1'])[n]) * site_op(o, int(para['index1'][n, 0]))
     for n in range(para['index2'].shape[0]):
         i, j, s1, s2 = [int(x) for x in para['index2'][n]]
-        h += float(para['coeff2'][n]) * site_op(np.real(ops[s1]), i) @ site_op(np.real(ops[s2]), j)
+        h += float(np.ravel(para['coeff2'])[n]) * site_op(np.real(ops[s1]), i) @ site_op(np.real(ops[s2]), j)
     return h
+
+
+# --------------------------------------------------------------------------------------------------
+# Two-site update (north_star kernels 1 + 3).  The reference's finite driver is one-site only; its two-site
+# machinery (library/MPSClass.py:1676-1707: theta contraction, term-summed matvec, SVD truncation) is used by iDMRG.
+# The oracle states the finite-size two-site algorithm through the DENSE Hamiltonian, so it shares no code path
+# with the product's grouped environments: H_eff = P^T H P with P the isometry of the two-site window.
+# --------------------------------------------------------------------------------------------------
+
+
+def two_site_isometry(mps, p):
+    """P[(s_0 .. s_{L-1}), (a, s_p, s_{p+1}, b)] for an MPS whose sites < p are left- and sites > p+1 right-orthogonal."""
+    L, d = len(mps), mps[0].shape[1]
+    left = np.ones((1, 1))                      # (config of sites < p, a)
+    for n in range(p):
+        t = mps[n]
+        left = np.einsum('ca,asb->csb', left, t).reshape(-1, t.shape[2])
+    right = np.ones((1, 1))                     # (b, config of sites > p+1)
+    for n in range(L - 1, p + 1, -1):
+        t = mps[n]
+        right = np.einsum('asb,bc->asc', t, right).reshape(t.shape[0], -1)
+    a, b = left.shape[1], right.shape[0]
+    eye = np.eye(d * d).reshape(d, d, d, d)     # (s_p s_{p+1}; s s')
+    iso = np.einsum('ca,xyst,bf->cxyfastb', left, eye, right)
+    return iso.reshape(d ** L, a * d * d * b)
+
+
+def dense_two_site_effective_hamiltonian(mps, p, para):
+    iso = two_site_isometry(mps, p)
+    return iso.T @ dense_hamiltonian(para) @ iso
+
+
+def dmrg_two_site_dense(para, chi, n_sweeps, seed=0, chi_init=2):
+    """finite two-site DMRG with dense local solves (small L): returns (energy, mps, lm list)."""
+    rng = np.random.RandomState(seed)
+    L, d = para['l'], para['d']
+    dims = [1] + [chi_init] * (L - 1) + [1]
+    mps = [rng.randn(dims[n], d, dims[n + 1]) for n in range(L)]
+    for n in range(L - 1, 0, -1):               # right-orthogonalise: centre at 0
+        mps[n], r, _, _ = decompose_r2l(mps[n], 'qr')
+        mps[n - 1] = mode_product(mps[n - 1], r, 2)
+    h = dense_hamiltonian(para)
+    lms, energy = [None] * (L - 1), None
+
+    def solve(p, to_right):
+        nonlocal energy
+        iso = two_site_isometry(mps, p)
+        w, v = np.linalg.eigh(iso.T @ h @ iso)
+        energy = w[0]
+        a, b = mps[p].shape[0], mps[p + 1].shape[2]
+        u, lm, vh = svd_truncate_two_site(v[:, 0].reshape(a, d, d, b), chi)
+        lm = lm / np.linalg.norm(lm)
+        lms[p] = lm
+        if to_right:
+            mps[p], mps[p + 1] = u, lm[:, None, None] * vh
+        else:
+            mps[p], mps[p + 1] = u * lm[None, None, :], vh
+
+    for _ in range(n_sweeps):
+        for p in range(L - 1):
+            solve(p, True)
+        for p in range(L - 2, -1, -1):
+            solve(p, False)
+    return energy, mps, lms

@@ -32,6 +32,44 @@ def _worker(rank, world, port, case, q):
         dist.destroy_process_group()
 
 
+def _worker_two_site(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from tests.cpu_backend import CpuBackend
+        from tests.test_two_site_cpu import small_para
+        from tnalg_b200 import ops
+        from tnalg_b200.DMRG_anyH import dmrg_finite_size_two_site
+        ops.set_backend(CpuBackend())
+        para = small_para('xxz', chi=16, sweep_time=6, dt_ob=1, break_tol=1e-13, eigs_tol=1e-14)
+        np.random.seed(1)
+        ob, A, info, para = dmrg_finite_size_two_site(para, chi_init=2)
+        q.put((rank, float(np.ravel(ob['e_per_site'])[0]), [lm.tolist() for lm in A.lm], [int(v) for v in A.virtual_dim]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_two_site_sweep_agree_with_exact_energy():
+    from oracle import dmrg_oracle as orc
+    from tests.test_two_site_cpu import small_para
+    world, port = 2, 31500 + os.getpid() % 2000
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_two_site, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, e0, lm0, vd0), (_, e1, lm1, vd1) = res
+    assert e0 == e1 and lm0 == lm1 and vd0 == vd1
+    para = small_para('xxz', chi=16)
+    exact = np.linalg.eigvalsh(orc.dense_hamiltonian(para))[0]
+    assert abs(e0 * para['l'] - exact) < 1e-10 * abs(exact) and max(vd0) == 16
+
+
 @pytest.mark.parametrize('case', ['e2e_j1j2_4x2'])
 def test_two_ranks_shard_terms_and_agree(case):
     world, port = 2, 29500 + os.getpid() % 2000

@@ -67,7 +67,7 @@ SHAPES = [(1, 2, 1), (2, 4, 2), (5, 6, 3), (16, 16, 16), (33, 18, 7), (64, 64, 6
 
 
 @pytest.mark.parametrize('mode', [0, 1, 2])
-@pytest.mark.parametrize('d', [1, 2, 3])
+@pytest.mark.parametrize('d', [1, 2, 3, 4])
 @pytest.mark.parametrize('deterministic', [1, 0])
 def test_chain_gemm_shapes(be, mode, d, deterministic):
     rng = np.random.RandomState(100 * mode + 10 * d + deterministic)
@@ -112,7 +112,7 @@ def test_chain_gemm_large_split_and_deterministic(be):
     assert np.array_equal(o_det1, o_det2)
 
 
-@pytest.mark.parametrize('shape', [(1, 2, 2), (2, 2, 4), (4, 2, 8), (16, 2, 16), (7, 3, 9), (64, 2, 32), (96, 2, 96), (130, 2, 128)])
+@pytest.mark.parametrize('shape', [(1, 2, 2), (2, 2, 4), (4, 2, 8), (16, 2, 16), (7, 3, 9), (64, 2, 32), (96, 2, 96), (130, 2, 128), (20, 4, 12)])
 def test_env_update_vs_oracle(be, shape):
     rng = np.random.RandomState(sum(shape))
     a, d, b = shape
@@ -172,7 +172,7 @@ def gpu_plan(be, shape, g, rank=0, world=1):
 
 @pytest.mark.parametrize('shape,counts', [((1, 2, 2), (0, 3, 0)), ((2, 2, 1), (3, 0, 0)), ((4, 2, 8), (3, 3, 2)), ((16, 2, 16), (3, 3, 0)),
                                           ((9, 3, 27), (2, 3, 4)), ((64, 2, 64), (3, 3, 9)), ((128, 2, 128), (3, 3, 5)),
-                                          ((256, 2, 256), (3, 3, 2)), ((100, 2, 60), (1, 2, 3))])
+                                          ((256, 2, 256), (3, 3, 2)), ((100, 2, 60), (1, 2, 3)), ((33, 4, 47), (4, 3, 5)), ((8, 4, 8), (2, 2, 1))])
 def test_matvec_vs_oracle(be, shape, counts):
     from tests.cpu_backend import CpuPlan
     rng = np.random.RandomState(sum(shape) + sum(counts))
@@ -194,7 +194,7 @@ def test_matvec_vs_oracle(be, shape, counts):
 
 
 @pytest.mark.parametrize('shape,counts', [((384, 2, 320), (3, 3, 10)), ((512, 2, 512), (3, 3, 4)), ((300, 2, 260), (2, 3, 9)),
-                                          ((258, 3, 264), (3, 2, 6)), ((640, 2, 192), (3, 3, 0))])
+                                          ((258, 3, 264), (3, 2, 6)), ((640, 2, 192), (3, 3, 0)), ((200, 4, 168), (4, 4, 7))])
 @pytest.mark.parametrize('tma', [True, False])
 def test_matvec_large_config_vs_oracle(be, shape, counts, tma, monkeypatch):
     """shapes that are scheduled on the 128x64 configuration: the TMA-staged kernel (default) and the cp.async kernel

@@ -73,6 +73,55 @@ def dmrg_finite_size(para=None, quiet=True):
     return ob, A, info, para
 
 
+def sweep_once_two_site(A, para, chi=None):
+    """left-to-right then right-to-left pass of two-site updates with SVD truncation to chi"""
+    L = para['l']
+    chi = para['chi'] if chi is None else chi
+    args = (para['index1'], para['index2'], para['coeff1'], para['coeff2'], para['tau'], para['is_real'])
+    for p in range(0, L - 1):
+        A.update_two_sites_eigs(p, *args, tol=para['eigs_tol'], chi=chi, to_right=True)
+    for p in range(L - 2, -1, -1):
+        A.update_two_sites_eigs(p, *args, tol=para['eigs_tol'], chi=chi, to_right=False)
+
+
+def dmrg_finite_size_two_site(para=None, chi_init=None, quiet=True):
+    """Finite-size DMRG with TWO-site updates and SVD truncation to para['chi'] (not in the reference's finite driver; it
+    combines the reference's term-summed two-site matvec and SVD truncation, library/MPSClass.py:1676-1707, with the sweep
+    of DMRG_anyH.py:18-101).  Same para dict and same (ob, A, info, para) return value as dmrg_finite_size; the MPS starts
+    at bond dimension chi_init (default min(chi, 4)) and grows to chi."""
+    t_start = time.time()
+    if para is None:
+        para = pm.generate_parameters_dmrg()
+    say = (lambda *a: None) if quiet else print
+    chi0 = min(para['chi'], 4) if chi_init is None else chi_init
+    A = Mob(length=para['l'], d=para['d'], chi=chi0, way='qr', ini_way='r', operators=para['op'], debug=is_debug,
+            is_parallel=para['isParallel'], par_pool=None, is_save_op=para['is_save_op'], eig_way=para['eigWay'],
+            is_env_parallel_lmr=para['isParallelEnvLMR'])
+    A.correct_orthogonal_center(0)
+    info = {'convergence': 1, 'n_sweeps': 0}
+    ob, e0 = dict(), 0
+    for t in range(0, para['sweep_time']):
+        if_ob = ((t + 1) % para['dt_ob'] == 0) or t == (para['sweep_time'] - 1)
+        sweep_once_two_site(A, para)
+        info['n_sweeps'] = t + 1
+        if if_ob:
+            observe(A, para, ob)
+            info['convergence'] = float(np.ravel(abs(ob['e_per_site'] - e0))[0])
+            if info['convergence'] < para['break_tol']:
+                say('Converged at the %d-th sweep with error = %g of energy per site.' % (t + 1, info['convergence']))
+                break
+            e0 = ob['e_per_site']
+    ob['eb'] = get_bond_energies(ob['eb_full'], para['positions_h2'], para['index2'])
+    A.calculate_entanglement_spectrum()
+    A.calculate_entanglement_entropy()
+    ob['corr_x'] = A.observe_correlators_from_middle(1, 1)
+    ob['corr_z'] = A.observe_correlators_from_middle(3, 3)
+    info['t_cost'] = time.time() - t_start
+    info.update({k: A.stats[k] for k in ('n_solves', 'n_matvec', 'flops_algorithmic', 'flops_executed', 'not_converged')})
+    A.clean_to_save()
+    return ob, A, info, para
+
+
 def get_bond_energies(eb_full, positions, index2):
     """sum the per-term energies onto their bond (DMRG_anyH.py:250-258)"""
     positions = np.asarray(positions)

@@ -347,6 +347,73 @@ class MpsOpenBoundaryClass(MpsBasic):
         if self.eig_way == 1:
             self.opt_env = dict()
 
+    # ---- two-site update with SVD truncation (north_star kernels 1 + 3; library/MPSClass.py:1676-1707 is the reference's
+    # two-site machinery, used there by iDMRG; here it drives a finite-size sweep with bond-dimension growth) ----
+    def update_two_sites_eigs(self, p, index1, index2, coeff1, coeff2, tau, is_real, tol=1e-16, chi=None, to_right=True):
+        """optimise theta = mps[p] . mps[p+1] as the dominant eigenvector of 1 - tau*H_eff(two sites) and split it back with
+        an SVD truncated to chi.  The centre ends on p+1 (to_right) or p."""
+        import torch
+        self._ensure_device()
+        be = self._be
+        if self.center < -0.5:
+            raise RuntimeError('CenterError: central-orthogonalize MPS before updating the tensor')
+        if not 0 <= p < self.length - 1:
+            raise ValueError('two-site update needs 0 <= p < length-1')
+        self.correct_orthogonal_center(p)
+        env = self._environments(index1, index2, coeff1, coeff2, tol)
+        dist = self._dist()
+        rank, world = (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
+        a, d, k = self.mps[p].shape
+        b = self.mps[p + 1].shape[2]
+        chi = self.virtual_dim.max() if chi is None else chi
+        plan = env.plan_two_site(p, self.mps, rank=rank, world=world)
+        # theta[(a s1), (s2 b)] = sum_k T_p[(a s1), k] T_{p+1}[k, (s2 b)]
+        theta = be.mode_product(self.mps[p].reshape(a * d, 1, k), self.mps[p + 1].reshape(k, d * b), 2)
+        allreduce = None
+        if dist is not None:
+            dev = be.device
+
+            def allreduce(buf, count, user, stream):
+                try:
+                    dist.all_reduce(_alias_tensor(buf, count, dev))
+                    return 0
+                except Exception:  # pragma: no cover
+                    return 1
+        if self.timing:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        lam, vec, n_mv, resid, ok = be.lanczos(plan, tau, theta.reshape(-1), tol, ncv=self.lanczos_ncv,
+                                               max_restarts=self.lanczos_max_restarts, allreduce=allreduce)
+        if self.timing:
+            e1.record()
+            self._events.append((e0, e1))
+        if dist is not None:
+            dist.broadcast(vec, src=0)
+        self.stats['n_solves'] += 1
+        self.stats['n_matvec'] += n_mv
+        self.stats['flops_algorithmic'] += n_mv * plan.flops_algorithmic
+        self.stats['flops_executed'] += n_mv * plan.flops_executed
+        self.stats['not_converged'] += 0 if ok else 1
+        self.last_eig = {'lambda': lam, 'residual': resid, 'n_matvec': n_mv, 'converged': ok}
+        plan.destroy()
+        kk = int(min(chi, a * d, d * b))
+        U, S, Vt = be.svd(vec.reshape(a * d, d * b), k_keep=kk)          # Jacobi SVD, truncated to chi
+        s_norm = be.norm(S)
+        self.last_eig['truncation_error'] = max(0.0, 1.0 - s_norm ** 2)   # discarded weight (the eigenvector has norm 1)
+        S = S / s_norm
+        if to_right:
+            self.mps[p] = U.contiguous().reshape(a, d, kk)
+            self.mps[p + 1] = be.scale_diag_rows(S, Vt).contiguous().reshape(kk, d, b)
+            self.center = p + 1
+            self.orthogonality[p], self.orthogonality[p + 1] = -1, 0
+        else:
+            self.mps[p] = (U * S[None, :]).contiguous().reshape(a, d, kk)
+            self.mps[p + 1] = Vt.contiguous().reshape(kk, d, b)
+            self.center = p
+            self.orthogonality[p], self.orthogonality[p + 1] = 0, 1
+        self.virtual_dim[p + 1] = kk
+        self.lm[p] = be.to_numpy(S)
+
     def solver_time_ms(self):
         """sum of the CUDA-event durations recorded by update_tensor_eigs while self.timing was True"""
         import torch

@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('TNALG_B200_LIB', os.path.join(HERE, 'libtnalg_b200.so'))  # override: kernel-variant experiments
 
-MAX_D = 3
+MAX_D = 4
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)

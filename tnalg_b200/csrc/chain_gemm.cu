@@ -69,7 +69,7 @@ struct SmemLayout {
   static constexpr int A_PITCH = A_COLS + PAD, B_PITCH = B_COLS + PAD;
   static constexpr int A_ELEMS = A_ROWS * A_PITCH, B_ELEMS = B_ROWS * B_PITCH;
   static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
-  static constexpr int OP_ELEMS = 4 * 16;  // ring of 4 link operators (9 entries + flag, padded to 16)
+  static constexpr int OP_ELEMS = 4 * kOpSlot;  // ring of 4 link operators
   static constexpr size_t BYTES = (size_t(STAGE_ELEMS) * Cfg::STAGES + OP_ELEMS) * sizeof(double);
 };
 
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) chain_gemm_kernel(con
           const LinkDev* L = p.links + p_link;
           Ag = L->a_dyn ? p.dyn_in : L->A;
           Bg = L->b_dyn ? p.dyn_in : L->B;
-          if (tid < 16) sOpRing[(p_link & 3) * 16 + tid] = tid < kMaxD * kMaxD ? L->op[tid] : (tid == 15 ? (double)L->has_op : 0.0);
+          if (tid < kOpSlot) sOpRing[(p_link & 3) * kOpSlot + tid] = tid < kMaxD * kMaxD ? L->op[tid] : (tid == kOpFlag ? (double)L->has_op : 0.0);
           li_cached = p_link;
           pa = Ag + a_off0 + p_k * a_kadv;
           pb = Bg + b_off0 + p_k * b_kadv;
@@ -336,8 +336,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) chain_gemm_kernel(con
       const double* sA = smem + stage * SL::STAGE_ELEMS;
       const double* sB = sA + SL::A_ELEMS;
       if (jj == 0 || c_k == 0) {  // first k-block of a link: pick up its operator
-        sO = sOpRing + (c_link & 3) * 16;
-        has_op = (d > 1) && (MODE != TN_TN) && (sO[15] != 0.0);
+        sO = sOpRing + (c_link & 3) * kOpSlot;
+        has_op = (d > 1) && (MODE != TN_TN) && (sO[kOpFlag] != 0.0);
       }
       if (++c_k == p.ipl) {
         c_k = 0;

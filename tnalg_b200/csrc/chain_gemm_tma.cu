@@ -38,7 +38,7 @@ constexpr int B_ELEMS = BN * BK;              // NT: two boxes of BN x 16; NN: f
 constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
 constexpr unsigned STAGE_BYTES = STAGE_ELEMS * sizeof(double);
 constexpr int kRing = STAGES + 2;  // operator ring: one slot per k-block in flight
-constexpr size_t SMEM_BYTES = size_t(STAGE_ELEMS) * STAGES * sizeof(double) + kRing * 16 * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+constexpr size_t SMEM_BYTES = size_t(STAGE_ELEMS) * STAGES * sizeof(double) + kRing * kOpSlot * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(THREADS, kTileCtas) chain_gemm_tma_kernel(cons
   extern __shared__ __align__(1024) double smem[];  // the swizzle pattern is a function of the shared address: 1024-byte aligned base
   if (smem_u32(smem) & 1023u) __trap();
   double* const sOpRing = smem + STAGE_ELEMS * STAGES;
-  uint64_t* const full = reinterpret_cast<uint64_t*>(sOpRing + kRing * 16);
+  uint64_t* const full = reinterpret_cast<uint64_t*>(sOpRing + kRing * kOpSlot);
   int* const done = reinterpret_cast<int*>(full + STAGES);  // per stage: consumer warps that finished reading it
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -199,9 +199,9 @@ __global__ void __launch_bounds__(THREADS, kTileCtas) chain_gemm_tma_kernel(cons
         li_cached = ps.link;
       }
       {  // operator of this k-block's link, one ring slot per k-block in flight
-        double* ring = sOpRing + (n_fill % kRing) * 16;
+        double* ring = sOpRing + (n_fill % kRing) * kOpSlot;
         const bool hop = (d > 1) && Lc->has_op;
-        ring[15] = hop ? 1.0 : 0.0;
+        ring[kOpFlag] = hop ? 1.0 : 0.0;
         if (hop) {
 #pragma unroll
           for (int i = 0; i < kMaxD * kMaxD; ++i) ring[i] = Lc->op[i];
@@ -307,8 +307,8 @@ __global__ void __launch_bounds__(THREADS, kTileCtas) chain_gemm_tma_kernel(cons
       mbar_wait(&full[stage], (n_cons / STAGES) & 1);
       const double* sA = smem + stage * STAGE_ELEMS;
       const double* sB = sA + A_ELEMS;
-      const double* sO = sOpRing + (n_cons % kRing) * 16;
-      const bool has_op = sO[15] != 0.0;
+      const double* sO = sOpRing + (n_cons % kRing) * kOpSlot;
+      const bool has_op = sO[kOpFlag] != 0.0;
       if (has_op) {
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) compute_kk(sA, sB, sO, true, kk);

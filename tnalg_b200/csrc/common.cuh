@@ -88,6 +88,9 @@ constexpr int kTileBM = TN_CFGL_BM, kTileBN = TN_CFGL_BN, kTileCtas = TN_CFGL_CT
 
 // ---- device-side descriptors of the chain GEMM (built by the host wrappers in chain_gemm.cu) ----
 constexpr int kMaxD = TN_MAX_PHYS_DIM;
+constexpr int kOpSlot = 24;   // doubles per operator slot in shared memory: kMaxD^2 entries + the has_op flag at [kOpFlag]
+constexpr int kOpFlag = 16;
+static_assert(kMaxD * kMaxD <= kOpFlag && kOpFlag < kOpSlot, "operator slot layout");
 
 struct LinkDev {
   const double* A;

@@ -221,12 +221,13 @@ class EnvCache:
         self.right[p] = new
         self.n_bond_moves += 1
 
-    def ensure(self, p, mps):
-        """make the left block of bond p and the right block of bond p+1 valid (centre at p)"""
+    def ensure(self, p, mps, width=1):
+        """make the left block of bond p and the right block of bond p+width valid (centre at p; width = 2 for the
+        two-site update)"""
         while self.lv < p:
             self._advance_left(self.lv, mps[self.lv])
             self.lv += 1
-        while self.rv > p + 1:
+        while self.rv > p + width:
             self._advance_right(self.rv - 1, mps[self.rv - 1])
             self.rv -= 1
 
@@ -267,6 +268,79 @@ class EnvCache:
                 g['x_coeff'].append(1.0)
         g['n_x_reference'] = len(cross)
         return g
+
+    # ---- two-site effective Hamiltonian of sites (p, p+1) ----
+    def groups_two_site(self, p, d):
+        """opt_env-style groups for the pair (p, p+1) acting on theta[a, (s1 s2), b] with the combined physical index
+        s = s1*d + s2 (dimension d*d): same six kinds of groups as the one-site case (MPSClass.py:684-733), with site
+        operators op (x) 1 / 1 (x) op and the in-pair terms folded into the on-site matrix M.  This is the term-summed
+        two-site matvec of the reference's White-style iDMRG (library/MPSClass.py:1688-1707) for an arbitrary term list."""
+        t, lb, rb = self.terms, self.left[p], self.right[p + 2]
+        P, Q, eye = p, p + 1, np.eye(d)
+        M = np.zeros((d * d, d * d))
+        has_m = False
+        for site, sn, c in t.one:
+            if site == P:
+                M += c * np.kron(t.ops[sn], eye)
+                has_m = True
+            elif site == Q:
+                M += c * np.kron(eye, t.ops[sn])
+                has_m = True
+        ls, rs, cross = {}, {}, []
+        for i, j, si, sj, c in t.two:
+            if i == P and j == Q:
+                M += c * np.kron(t.ops[si], t.ops[sj])
+                has_m = True
+            elif j == P:
+                ls.setdefault((0, sj), []).append((c, (i, si)))
+            elif j == Q and i < P:
+                ls.setdefault((1, sj), []).append((c, (i, si)))
+            elif i == P and j > Q:
+                rs.setdefault((0, si), []).append((c, (j, sj)))
+            elif i == Q and j > Q:
+                rs.setdefault((1, si), []).append((c, (j, sj)))
+            elif i < P and j > Q:
+                cross.append((c, (i, si), (j, sj)))
+
+        def pair_op(slot, sn):
+            return np.kron(t.ops[sn], eye) if slot == 0 else np.kron(eye, t.ops[sn])
+
+        g = {'HL': lb['H'], 'HR': rb['H'], 'M': M if has_m else None, 'LS': [], 'ls_ops': [], 'RS': [], 'rs_ops': [],
+             'XL': [], 'XR': [], 'x_coeff': []}
+        for (slot, sn), pairs in sorted(ls.items()):
+            g['LS'].append(self._lincomb(lb, pairs))
+            g['ls_ops'].append(pair_op(slot, sn))
+        for (slot, sn), pairs in sorted(rs.items()):
+            g['RS'].append(self._lincomb(rb, pairs))
+            g['rs_ops'].append(pair_op(slot, sn))
+        by_left, by_right = {}, {}
+        for c, lk, rk in cross:
+            by_left.setdefault(lk, []).append((c, rk))
+            by_right.setdefault(rk, []).append((c, lk))
+        if len(by_left) <= len(by_right):
+            for lk in sorted(by_left):
+                g['XL'].append(lb['O'][lk])
+                g['XR'].append(self._lincomb(rb, by_left[lk]))
+                g['x_coeff'].append(1.0)
+        else:
+            for rk in sorted(by_right):
+                g['XL'].append(self._lincomb(lb, by_right[rk]))
+                g['XR'].append(rb['O'][rk])
+                g['x_coeff'].append(1.0)
+        g['n_x_reference'] = len(cross)
+        return g
+
+    def plan_two_site(self, p, mps, rank=0, world=1):
+        self.ensure(p, mps, width=2)
+        a, d, _ = mps[p].shape
+        b = mps[p + 1].shape[2]
+        g = self.groups_two_site(p, d)
+        plan = self.be.effh_plan((a, d * d, b), g['HL'], g['HR'], g['M'], g['LS'], g['ls_ops'], g['RS'], g['rs_ops'],
+                                 g['XL'], g['XR'], g['x_coeff'], rank=rank, world=world)
+        kl = (1 if g['HL'] is not None else 0) + len(g['LS'])
+        kr = (1 if g['HR'] is not None else 0) + len(g['RS'])
+        plan.flops_algorithmic = 2.0 * a * d * d * b * (a * (kl + g['n_x_reference']) + b * (kr + g['n_x_reference']))
+        return plan
 
     def plan(self, p, mps, rank=0, world=1):
         self.ensure(p, mps)
