@@ -274,7 +274,8 @@ def test_lanczos_vs_dense_eigh(be, shape, counts, tol, fused, monkeypatch):
     assert n_mv >= min(n, 2)
 
 
-@pytest.mark.parametrize('shape', [(1, 1), (2, 1), (1, 5), (4, 4), (8, 3), (3, 8), (37, 21), (64, 64), (130, 64), (64, 130), (256, 128)])
+@pytest.mark.parametrize('shape', [(1, 1), (2, 1), (1, 5), (4, 4), (8, 3), (3, 8), (37, 21), (64, 64), (130, 64), (64, 130), (256, 128),
+                                   (33, 33), (100, 70), (512, 512), (700, 260)])
 def test_svd_jacobi_vs_lapack(be, shape):
     rng = np.random.RandomState(shape[0] * 7 + shape[1])
     m, n = shape
@@ -312,6 +313,33 @@ def test_svd_ill_conditioned_preconditioned(be):
     assert np.abs((U * S) @ Vt - A).max() < 1e-13
     U0, S0, Vt0 = [be.to_numpy(x) for x in be.svd(be.from_numpy(A), precondition=False)]
     assert np.abs(S0 - s).max() < 1e-10 and be.last_svd_sweeps > 14
+
+
+@pytest.mark.parametrize('shape', [(5, 3), (64, 64), (130, 64), (300, 300)])
+def test_svd_unblocked_kernel_agrees(be, shape, monkeypatch):
+    """the unblocked kernel (rows in global memory; used when two rows do not fit shared memory) gives the same SVD"""
+    rng = np.random.RandomState(shape[0] + shape[1])
+    A = rng.randn(*shape)
+    U, S, Vt = [be.to_numpy(x) for x in be.svd(be.from_numpy(A))]
+    monkeypatch.setenv('TNALG_SVD_UNBLOCKED', '1')
+    U0, S0, Vt0 = [be.to_numpy(x) for x in be.svd(be.from_numpy(A))]
+    s_ref = np.linalg.svd(A, compute_uv=False)
+    assert np.abs(S - s_ref).max() < 1e-13 * s_ref.max() and np.abs(S0 - s_ref).max() < 1e-13 * s_ref.max()
+    assert np.abs((U * S) @ Vt - A).max() < 1e-12 and np.abs((U0 * S0) @ Vt0 - A).max() < 1e-12
+
+
+def test_svd_rank_deficient_two_site_wavefunction(be):
+    """theta of a two-site update: numerical rank chi out of 2*chi, the rest is round-off -- kept triplets exact, all
+    vectors orthonormal, convergence within the sweep budget"""
+    rng = np.random.RandomState(12)
+    chi = 96
+    s = np.concatenate([np.logspace(0, -9, chi), 1e-17 * rng.rand(chi)])
+    A = (np.linalg.qr(rng.randn(2 * chi, 2 * chi))[0] * s) @ np.linalg.qr(rng.randn(2 * chi, 2 * chi))[0].T
+    U, S, Vt = [be.to_numpy(x) for x in be.svd(be.from_numpy(A), k_keep=chi)]
+    assert be.last_svd_sweeps <= 20
+    assert np.abs(S[:chi // 2] / s[:chi // 2] - 1).max() < 1e-9 and np.abs(S - s[:chi]).max() < 1e-14
+    assert np.abs(U.T @ U - np.eye(chi)).max() < 1e-12 and np.abs(Vt @ Vt.T - np.eye(chi)).max() < 1e-12
+    assert np.abs((U * S) @ Vt - A).max() < 1e-13
 
 
 def test_svd_matches_cusolver_baseline(be):

@@ -59,16 +59,32 @@ def test_two_site_truncated_sweep_matches_dense_solve_dmrg():
     assert np.abs(np.asarray(A.lm[mid]) - sv).max() < 1e-8
 
 
-def test_two_site_j1j2_4x4_chi32_variational_and_normalised():
-    """larger window sizes (a = b = 32, d*d = 4): energy is variational w.r.t. ED of the 16-site cluster and improves on chi"""
-    from tnalg_b200 import DMRG_anyH, Parameters as Pm
-    import scipy.sparse.linalg as sla
-    para = dict(orc.j1j2_square_para(4, 3, j1=1.0, j2=0.5))
-    para.update(chi=32, sweep_time=4, dt_ob=1, break_tol=1e-9, eigs_tol=1e-12)
+def test_two_site_j1j2_4x2_truncated_is_variational():
+    from tnalg_b200 import DMRG_anyH
+    para = dict(orc.j1j2_square_para(4, 2, j1=1.0, j2=0.5))
+    para.update(chi=8, sweep_time=6, dt_ob=1, break_tol=1e-10, eigs_tol=1e-12)
     np.random.seed(4)
-    ob, A, info, _ = DMRG_anyH.dmrg_finite_size_two_site(para, chi_init=4)
+    ob, A, info, _ = DMRG_anyH.dmrg_finite_size_two_site(para, chi_init=2)
     e = float(np.ravel(ob['e_per_site'])[0]) * para['l']
-    e0 = np.linalg.eigvalsh(orc.dense_hamiltonian(para))[0] if para['l'] <= 12 else None
-    assert e0 is not None and e >= e0 - 1e-9 and (e - e0) < 2e-3 * abs(e0)
-    assert max(A.virtual_dim) == 32 and info['not_converged'] == 0
-    assert all(abs(np.linalg.norm(lm) - 1) < 1e-10 for lm in A.lm if np.size(lm))
+    e0 = np.linalg.eigvalsh(orc.dense_hamiltonian(para))[0]
+    e_ref, _, _ = orc.dmrg_two_site_dense(para, 8, 10, seed=1)     # dense-solve two-site DMRG at the same chi
+    assert e >= e0 - 1e-10 and abs(e - e_ref) < 1e-10 * abs(e_ref)
+    assert max(A.virtual_dim) == 8 and info['not_converged'] == 0
+
+
+def test_two_site_chain20_chi32_agrees_with_one_site_sweep():
+    """window sizes a = b = 32 with d*d = 4: the two-site and the one-site sweep at the same chi reach the same energy"""
+    from tnalg_b200 import DMRG_anyH, Parameters as Pm
+    para = Pm.generate_parameters_dmrg('chain')
+    para.update(l=20, chi=32, sweep_time=6, dt_ob=1, break_tol=1e-11, eigs_tol=1e-13)
+    para = Pm.make_consistent_parameter_dmrg(para)
+    np.random.seed(6)
+    ob2, A2, info2, _ = DMRG_anyH.dmrg_finite_size_two_site(dict(para), chi_init=4)
+    np.random.seed(6)
+    ob1, A1, info1, _ = DMRG_anyH.dmrg_finite_size(dict(para))
+    e1, e2 = float(np.ravel(ob1['e_per_site'])[0]), float(np.ravel(ob2['e_per_site'])[0])
+    assert abs(e1 - e2) < 1e-6 * abs(e1), (e1, e2)
+    assert max(A2.virtual_dim) == 32 and info2['not_converged'] == 0
+    assert all(abs(np.linalg.norm(lm) - 1) < 1e-10 for lm in A2.lm if np.size(lm))
+    mid = para['l'] // 2 - 1
+    assert np.abs(np.asarray(A1.lm[mid])[:8] - np.asarray(A2.lm[mid])[:8]).max() < 1e-4

@@ -106,7 +106,7 @@ __device__ __forceinline__ void load_kn(double* s, const double* g, long long ld
   }
 }
 
-template <class Cfg, int MODE, bool A16>
+template <class Cfg, int MODE, bool A16, int DMAX>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) chain_gemm_kernel(const GemmParams p) {
   using SL = SmemLayout<Cfg, MODE>;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, WM = Cfg::WM, WN = Cfg::WN, STAGES = Cfg::STAGES;
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) chain_gemm_kernel(con
         } else if (MODE == TN_NT && has_op) {
           double v = 0.0;
 #pragma unroll
-          for (int sp = 0; sp < kMaxD; ++sp)
+          for (int sp = 0; sp < DMAX; ++sp)
             if (sp < d) v += sO[m_s[mt] * d + sp] * sA[(m_base[mt] + sp) * SL::A_PITCH + kc];
           a[mt] = v;
         } else {
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) chain_gemm_kernel(con
         } else if (MODE == TN_NN && has_op) {
           double v = 0.0;
 #pragma unroll
-          for (int sp = 0; sp < kMaxD; ++sp)
+          for (int sp = 0; sp < DMAX; ++sp)
             if (sp < d) v += sO[n_s[nt] * d + sp] * sB[kc * SL::B_PITCH + sp * BNy + n_y[nt]];
           b[nt] = v;
         } else {
@@ -414,11 +414,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) chain_gemm_kernel(con
 using CfgL = TileCfg<TN_CFGL_BM, TN_CFGL_BN, 32, TN_CFGL_WN, TN_STAGES_L, TN_CFGL_CTAS>;  // default: 4 warps of 32x64, 64 accumulator doubles per thread
 using CfgS = TileCfg<64, 64, 32, 32, (TN_BK > 16 ? 3 : 4)>;    // 128 threads, 32 accumulator doubles per thread
 
-template <class Cfg, int MODE, bool A16>
+template <class Cfg, int MODE, bool A16, int DMAX>
 static int launch_one(const GemmParams& p, int grid, cudaStream_t stream) {
   using SL = SmemLayout<Cfg, MODE>;
   static bool configured = false;
-  auto kern = chain_gemm_kernel<Cfg, MODE, A16>;
+  auto kern = chain_gemm_kernel<Cfg, MODE, A16, DMAX>;
   if (!configured) {
     TN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::BYTES));
     configured = true;
@@ -431,9 +431,10 @@ static int launch_one(const GemmParams& p, int grid, cudaStream_t stream) {
 template <class Cfg, bool A16>
 static int launch_mode(int mode, const GemmParams& p, int grid, cudaStream_t stream) {
   switch (mode) {
-    case TN_NN: return launch_one<Cfg, TN_NN, A16>(p, grid, stream);
-    case TN_NT: return launch_one<Cfg, TN_NT, A16>(p, grid, stream);
-    case TN_TN: return launch_one<Cfg, TN_TN, A16>(p, grid, stream);
+    // operator loops unrolled to 2 (spin-1/2) or kMaxD (spin-1, two-site window); TN carries no operator
+    case TN_NN: return p.d > 2 ? launch_one<Cfg, TN_NN, A16, kMaxD>(p, grid, stream) : launch_one<Cfg, TN_NN, A16, 2>(p, grid, stream);
+    case TN_NT: return p.d > 2 ? launch_one<Cfg, TN_NT, A16, kMaxD>(p, grid, stream) : launch_one<Cfg, TN_NT, A16, 2>(p, grid, stream);
+    case TN_TN: return launch_one<Cfg, TN_TN, A16, 2>(p, grid, stream);
   }
   set_error("chain_gemm: unknown mode %d", mode);
   return TN_ERR_INVALID;

@@ -70,7 +70,7 @@ __device__ __forceinline__ void tma_3d(void* dst, const CUtensorMap* map, int c0
 
 // psi_map_a: psi as the (M = a*d) x (K = b) A operand of the right stage (2-D, box 16 x BM)
 // psi_map_b: psi as the (K = a') x (s) x (y = b) B operand of the left stage (3-D, box 16 x 1 x BK)
-template <int MODE>
+template <int MODE, int DMAX>
 __global__ void __launch_bounds__(THREADS, kTileCtas) chain_gemm_tma_kernel(const GemmParams p, const CUtensorMap* __restrict__ maps,
                                                                     const __grid_constant__ CUtensorMap psi_map_a,
                                                                     const __grid_constant__ CUtensorMap psi_map_b) {
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(THREADS, kTileCtas) chain_gemm_tma_kernel(cons
         ring[kOpFlag] = hop ? 1.0 : 0.0;
         if (hop) {
 #pragma unroll
-          for (int i = 0; i < kMaxD * kMaxD; ++i) ring[i] = Lc->op[i];
+          for (int i = 0; i < DMAX * DMAX; ++i) ring[i] = Lc->op[i];
         }
       }
       double* sA = smem + stage * STAGE_ELEMS;
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(THREADS, kTileCtas) chain_gemm_tma_kernel(cons
         if (MODE == TN_NT && has_op) {
           double v = 0.0;
 #pragma unroll
-          for (int sp = 0; sp < kMaxD; ++sp)
+          for (int sp = 0; sp < DMAX; ++sp)
             if (sp < d) {
               const int rr = m_base[mt] + sp;
               v += sO[m_s[mt] * d + sp] * sA[h * (BM * BOXW) + rr * BOXW + ((atom ^ (rr & 3)) << 2) + t];
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(THREADS, kTileCtas) chain_gemm_tma_kernel(cons
           if (has_op) {
             double v = 0.0;
 #pragma unroll
-            for (int sp = 0; sp < kMaxD; ++sp)
+            for (int sp = 0; sp < DMAX; ++sp)
               if (sp < d) {
                 const int cc = sp * BNy + n_y[nt];
                 v += sO[n_s[nt] * d + sp] * sB[(cc >> 4) * (BK * BOXW) + k * BOXW + ((((cc & 15) >> 2) ^ t) << 2) + (cc & 3)];
@@ -450,17 +450,25 @@ int gemm_launch_tma(const GemmLaunch& L, const GemmSchedule& S, const ProblemDev
   p.dyn_in = dyn_in; p.dyn_out = dyn_out; p.dyn_alpha = dyn_alpha;
   static bool configured = false;
   if (!configured) {
-    TN_CUDA(cudaFuncSetAttribute(chain_gemm_tma_kernel<TN_NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    TN_CUDA(cudaFuncSetAttribute(chain_gemm_tma_kernel<TN_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    TN_CUDA(cudaFuncSetAttribute(chain_gemm_tma_kernel<TN_NN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    TN_CUDA(cudaFuncSetAttribute(chain_gemm_tma_kernel<TN_NT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    TN_CUDA(cudaFuncSetAttribute(chain_gemm_tma_kernel<TN_NN, kMaxD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    TN_CUDA(cudaFuncSetAttribute(chain_gemm_tma_kernel<TN_NT, kMaxD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     configured = true;
   }
   const CUtensorMap* md = reinterpret_cast<const CUtensorMap*>(maps_dev);
   const CUtensorMap& pa = reinterpret_cast<const CUtensorMap&>(psi_a);
   const CUtensorMap& pb = reinterpret_cast<const CUtensorMap&>(psi_b);
-  if (L.mode == TN_NN)
-    chain_gemm_tma_kernel<TN_NN><<<S.grid, THREADS, SMEM_BYTES, stream>>>(p, md, pa, pb);
-  else
-    chain_gemm_tma_kernel<TN_NT><<<S.grid, THREADS, SMEM_BYTES, stream>>>(p, md, pa, pb);
+  // the operator loops are unrolled to the physical dimension bound: d <= 2 (spin-1/2, the headline case) keeps the lean
+  // instantiation, d = 3 (spin-1) and d = 4 (two-site window of spin-1/2) use the wide one
+  const bool wide = L.d > 2;
+  if (L.mode == TN_NN) {
+    if (wide) chain_gemm_tma_kernel<TN_NN, kMaxD><<<S.grid, THREADS, SMEM_BYTES, stream>>>(p, md, pa, pb);
+    else chain_gemm_tma_kernel<TN_NN, 2><<<S.grid, THREADS, SMEM_BYTES, stream>>>(p, md, pa, pb);
+  } else {
+    if (wide) chain_gemm_tma_kernel<TN_NT, kMaxD><<<S.grid, THREADS, SMEM_BYTES, stream>>>(p, md, pa, pb);
+    else chain_gemm_tma_kernel<TN_NT, 2><<<S.grid, THREADS, SMEM_BYTES, stream>>>(p, md, pa, pb);
+  }
   TN_LAUNCHED();
   return TN_OK;
 }

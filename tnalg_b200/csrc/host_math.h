@@ -79,9 +79,22 @@ TN_HD inline int tridiag_ql_rows(int n, double* d, double* e, double* z, int ldz
 // One-sided Jacobi rotation for the column pair with squared norms (alpha, beta) and inner product gamma:
 // returns (c, s) such that  p' = c p - s q,  q' = s p + c q  are orthogonal.
 TN_HD inline void jacobi_rotation(double alpha, double beta, double gamma, double* c, double* s) {
-  const double zeta = (beta - alpha) / (2.0 * gamma);
-  const double t = tn_sign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+  // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)),  zeta = (beta - alpha) / (2 gamma), written with one sqrt, one division
+  // and one reciprocal sqrt (the rotation is on the latency-critical path of every Jacobi round)
+  const double dd = beta - alpha;
+  const double r = sqrt(dd * dd + 4.0 * gamma * gamma);
+  double t;
+  if (r > 0.0 && r < 1e300) {
+    t = 2.0 * gamma / (dd + tn_sign(r, dd));
+  } else {  // squares under- or overflowed: the scale-free form
+    const double zeta = dd / (2.0 * gamma);
+    t = tn_sign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+  }
+#ifdef __CUDA_ARCH__
+  *c = rsqrt(1.0 + t * t);
+#else
   *c = 1.0 / sqrt(1.0 + t * t);
+#endif
   *s = *c * t;
 }
 

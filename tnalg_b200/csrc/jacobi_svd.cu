@@ -4,12 +4,19 @@
 //   m >= n : W = A^T (n rows of length m), the accumulated rotations give V^T, U = normalised rows
 //   m <  n : W = A   (m rows of length n), the accumulated rotations give U^T, V^T = normalised rows
 // so every dot product and every rotation streams over contiguous memory (coalesced, HBM/L2-bound).
-// One kernel launch per round of the round-robin (chess tournament) ordering: r/2 disjoint pairs, one CTA per
-// pair, warp-shuffle reductions for (|p|^2, |q|^2, p.q).  The sweep loop stops when a whole sweep applied no
-// rotation.  Singular values are sorted on the host (k doubles), the gather of the k_keep leading triplets is a
+// Blocked schedule (default): the rows are cut into blocks of w rows; one launch per round of a round-robin (chess
+// tournament) over the BLOCKS, one CTA per block pair.  The CTA stages its 2w rows of W and of the rotation accumulator
+// in shared memory with 1-D bulk copies (cp.async.bulk + mbarrier), rotates every row pair between the two blocks there
+// (w rounds of w disjoint pairs, 16/w warps per pair, warp-shuffle reductions for |p|^2, |q|^2, p.q) and bulk-stores
+// the rows back: each global round trip serves w^2 rotations instead of one and a sweep needs rows/w - 1 launches
+// instead of rows - 1.  Pairs inside a block are rotated in the first round of every sweep.  w is the largest power of
+// two whose 2w rows fit 200 KB of shared memory (w = 8 for 512 rows with vectors, 4 for 1024, 2 for 2048); rows too
+// long for that use the unblocked kernel (one CTA per row pair, rows in global memory / L2).
+// The sweep loop stops when a whole sweep applied no rotation.  Singular values are sorted on the host (k doubles), the gather of the k_keep leading triplets is a
 // kernel.  Jacobi gives high relative accuracy for the small Schmidt values the entanglement spectrum needs.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <numeric>
 #include <vector>
 
@@ -86,6 +93,168 @@ __global__ void __launch_bounds__(kJacThreads) jacobi_round_kernel(double* __res
       ap[e] = c * x - s * y;
       aq[e] = s * x + c * y;
     }
+  }
+}
+
+
+// ---- blocked variant: 2w rows resident in shared memory ----
+constexpr int kBlkThreads = 512;
+constexpr int kBlkWarps = kBlkThreads / 32;
+constexpr size_t kBlkSmemBudget = 200 * 1024;
+
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+
+// chess-tournament pair i (0 <= i < rows/2) of round `round` (0 <= round < rows-1), rows even
+__host__ __device__ __forceinline__ void tournament_pair(int rows, int round, int i, int* p, int* q) {
+  const int nm1 = rows - 1;
+  int a, b;
+  if (i == 0) {
+    a = round % nm1;
+    b = nm1;
+  } else {
+    a = (round + i) % nm1;
+    b = (round + nm1 - i) % nm1;
+  }
+  *p = a < b ? a : b;
+  *q = a < b ? b : a;
+}
+
+// W: rp x ldw, Acc: rp x lda (or null), rp = nb*w rows, nb even.  Launch nb/2 CTAs for block round `round` in
+// [0, nb-1).  full != 0: also rotate the pairs inside each block (first round of a sweep).
+__global__ void __launch_bounds__(kBlkThreads, 1) jacobi_block_kernel(double* __restrict__ W, int ldw, int len, double* __restrict__ Acc, int lda,
+                                                                      int w, int nb, int round, int full, double tol, unsigned* n_rot) {
+  extern __shared__ __align__(128) double sm[];
+  const int acc_len = Acc ? lda : 0;
+  const int rowlen = ldw + acc_len;
+  double* part = sm + (size_t)2 * w * rowlen;                       // [w pairs][kBlkWarps][3]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(part + w * kBlkWarps * 3);
+  int* any_rot = reinterpret_cast<int*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int bi, bj;
+  tournament_pair(nb, round, blockIdx.x, &bi, &bj);
+  auto grow = [&](int r) { return (long long)(r < w ? bi * w + r : bj * w + (r - w)); };
+
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    *any_rot = 0;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"((unsigned)(2 * w * rowlen * sizeof(double)))
+                   : "memory");
+    __syncwarp();
+    for (int r = lane; r < 2 * w; r += 32) {
+      const long long gr = grow(r);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(sm + (size_t)r * rowlen)),
+                   "l"(W + gr * ldw), "r"((unsigned)(ldw * sizeof(double))), "r"(smem_addr(bar))
+                   : "memory");
+      if (acc_len)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_addr(sm + (size_t)r * rowlen + ldw)),
+                     "l"(Acc + gr * lda), "r"((unsigned)(lda * sizeof(double))), "r"(smem_addr(bar))
+                     : "memory");
+    }
+  }
+  asm volatile(
+      "{\n.reg .pred p;\nTN_JWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+      "@!p bra TN_JWAIT_%=;\n}\n" ::"r"(smem_addr(bar))
+      : "memory");
+
+  const int wpp = kBlkWarps / w;          // warps per row pair
+  const int pr = warp / wpp, sw = warp % wpp;
+  const int n_rounds = full ? 2 * w - 1 : w;
+  unsigned my_rot = 0;
+  for (int r = 0; r < n_rounds; ++r) {
+    int p, q;
+    if (full) {
+      tournament_pair(2 * w, r, pr, &p, &q);
+    } else {
+      p = pr;
+      q = w + (pr + r) % w;
+    }
+    double* rp_ = sm + (size_t)p * rowlen;
+    double* rq_ = sm + (size_t)q * rowlen;
+    // rows are 16-byte aligned and zero-padded to an even length: double2 accesses, four independent loads in flight
+    double2* const p2 = reinterpret_cast<double2*>(rp_);
+    double2* const q2 = reinterpret_cast<double2*>(rq_);
+    const int stride = 32 * wpp, e0 = sw * 32 + lane;
+    double a = 0.0, b = 0.0, g = 0.0;
+    {
+      const int n2 = ldw >> 1;
+      int e = e0;
+      for (; e + 3 * stride < n2; e += 4 * stride) {
+        double2 x[4], y[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { x[u] = p2[e + u * stride]; y[u] = q2[e + u * stride]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          a += x[u].x * x[u].x + x[u].y * x[u].y;
+          b += y[u].x * y[u].x + y[u].y * y[u].y;
+          g += x[u].x * y[u].x + x[u].y * y[u].y;
+        }
+      }
+      for (; e < n2; e += stride) {
+        const double2 x = p2[e], y = q2[e];
+        a += x.x * x.x + x.y * x.y;
+        b += y.x * y.x + y.y * y.y;
+        g += x.x * y.x + x.y * y.y;
+      }
+    }
+    a = warp_sum_j(a); b = warp_sum_j(b); g = warp_sum_j(g);
+    if (wpp > 1) {  // CTA-uniform
+      if (lane == 0) {
+        double* o = part + (pr * kBlkWarps + sw) * 3;
+        o[0] = a; o[1] = b; o[2] = g;
+      }
+      __syncthreads();
+      a = b = g = 0.0;
+      for (int k = 0; k < wpp; ++k) {  // fixed order: every warp of the pair gets bit-identical sums
+        const double* o = part + (pr * kBlkWarps + k) * 3;
+        a += o[0]; b += o[1]; g += o[2];
+      }
+    }
+    if (a > 0.0 && b > 0.0 && g * g > (tol * tol) * a * b) {  // warp-uniform; |g| > tol |p| |q| without the square roots
+      double c, s;
+      jacobi_rotation(a, b, g, &c, &s);
+      const int n2 = rowlen >> 1;
+      int e = e0;
+      for (; e + 3 * stride < n2; e += 4 * stride) {
+        double2 x[4], y[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { x[u] = p2[e + u * stride]; y[u] = q2[e + u * stride]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          p2[e + u * stride] = make_double2(c * x[u].x - s * y[u].x, c * x[u].y - s * y[u].y);
+          q2[e + u * stride] = make_double2(s * x[u].x + c * y[u].x, s * x[u].y + c * y[u].y);
+        }
+      }
+      for (; e < n2; e += stride) {
+        const double2 x = p2[e], y = q2[e];
+        p2[e] = make_double2(c * x.x - s * y.x, c * x.y - s * y.y);
+        q2[e] = make_double2(s * x.x + c * y.x, s * x.y + c * y.y);
+      }
+      if (sw == 0 && lane == 0) { ++my_rot; *any_rot = 1; }
+    }
+    __syncthreads();
+  }
+  if (my_rot) atomicAdd(n_rot, my_rot);
+  if (*any_rot && warp == 0) {  // write the rows back (generic-proxy smem writes -> async-proxy reads need the fence)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int r = lane; r < 2 * w; r += 32) {
+      const long long gr = grow(r);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(W + gr * ldw), "r"(smem_addr(sm + (size_t)r * rowlen)),
+                   "r"((unsigned)(ldw * sizeof(double)))
+                   : "memory");
+      if (acc_len)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(Acc + gr * lda),
+                     "r"(smem_addr(sm + (size_t)r * rowlen + ldw)), "r"((unsigned)(lda * sizeof(double)))
+                     : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 }
 
@@ -168,26 +337,56 @@ __global__ void gather_sig_kernel(const double* sig, const int* perm, int k, dou
 
 using namespace tn;
 
-static void svd_dims(int m, int n, int* rows, int* rows_pad, int* len) {
-  *rows = std::min(m, n);
-  *len = std::max(m, n);
-  *rows_pad = (*rows + 1) / 2 * 2;
+struct SvdGeom {
+  int rows, len, w, rp;   // w = block rows of the shared-memory schedule (0: unblocked kernel), rp = padded row count
+  long long ldw;
+  size_t smem;
+};
+
+static size_t block_smem_bytes(int w, long long rowlen) {
+  return sizeof(double) * ((size_t)2 * w * rowlen + (size_t)w * kBlkWarps * 3) + 16;
+}
+
+static SvdGeom svd_geom(int m, int n) {
+  SvdGeom g;
+  g.rows = std::min(m, n);
+  g.len = std::max(m, n);
+  g.ldw = (long long)(g.len + 1) / 2 * 2;
+  g.w = 0;
+  g.rp = (g.rows + 1) / 2 * 2;
+  g.smem = 0;
+  const char* e = getenv("TNALG_SVD_UNBLOCKED");
+  if (e && e[0] == '1') return g;
+  int w0 = 16;
+  while (w0 > 1 && w0 >= g.rows) w0 >>= 1;
+  for (int w = w0; w >= 1; w >>= 1) {
+    const int rp = (g.rows + 2 * w - 1) / (2 * w) * (2 * w);
+    const size_t bytes = block_smem_bytes(w, g.ldw + rp);
+    if (bytes <= kBlkSmemBudget) {
+      // measured on B200 (profiles/r01_svd.md): with w < 4 the staging cost per launch outweighs the saved launches
+      if (w < 4 && g.rows > 64) break;
+      g.w = w;
+      g.rp = rp;
+      g.smem = bytes;
+      break;
+    }
+  }
+  return g;
 }
 
 extern "C" size_t tn_svd_workspace_bytes(int m, int n) {
-  int rows, rp, len;
-  svd_dims(m, n, &rows, &rp, &len);
-  size_t ldw = (size_t)(len + 1) / 2 * 2;
-  return align_up(sizeof(double) * (size_t)rp * ldw) + align_up(sizeof(double) * (size_t)rp * rp) + align_up(sizeof(double) * rp) +
-         align_up(sizeof(int) * (size_t)rp) + align_up(sizeof(unsigned)) + 1024;
+  const SvdGeom g = svd_geom(m, n);
+  const size_t rp = (size_t)g.rp + 32;  // the geometry may differ by the TNALG_SVD_UNBLOCKED switch: cover both
+  return align_up(sizeof(double) * rp * (size_t)g.ldw) + align_up(sizeof(double) * rp * rp) + align_up(sizeof(double) * rp) +
+         align_up(sizeof(int) * rp) + align_up(sizeof(unsigned)) + 1024;
 }
 
 extern "C" int tn_svd_jacobi(const double* A, int m, int n, int k_keep, double* U, double* S, double* Vt, int* sweeps_out,
                              void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   TN_REQUIRE(A && S && m > 0 && n > 0, "tn_svd_jacobi: bad arguments");
-  int rows, rp, len;
-  svd_dims(m, n, &rows, &rp, &len);
+  const SvdGeom geo = svd_geom(m, n);
+  const int rows = geo.rows, rp = geo.rp, len = geo.len;
   TN_REQUIRE(k_keep >= 1 && k_keep <= rows, "tn_svd_jacobi: k_keep=%d not in 1..%d", k_keep, rows);
   TN_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "tn_svd_jacobi: workspace must be 256-byte aligned");
   if (workspace_bytes < tn_svd_workspace_bytes(m, n)) {
@@ -217,15 +416,31 @@ extern "C" int tn_svd_jacobi(const double* A, int m, int n, int k_keep, double* 
     set_identity_kernel<<<std::min(1024, (rp * rp + 255) / 256), 256, 0, stream>>>(Acc, rp, rp);
     TN_LAUNCHED();
   }
+  if (geo.w > 0) {
+    static bool configured = false;
+    if (!configured) {
+      TN_CUDA(cudaFuncSetAttribute(jacobi_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      configured = true;
+    }
+  }
   const double tol = std::max(1e-15, std::sqrt((double)len) * 2.2e-16);
   int sweeps = 0;
   const int max_sweeps = 80;  // QR-preconditioned inputs (ops.CudaBackend.svd) need ~8; raw ill-conditioned ones 20-50
   bool converged = rp < 2;
   while (!converged && sweeps < max_sweeps) {
     TN_CUDA(cudaMemsetAsync(n_rot, 0, sizeof(unsigned), stream));
-    for (int round = 0; round < rp - 1; ++round) {
-      jacobi_round_kernel<<<rp / 2, kJacThreads, 0, stream>>>(W, ldw, len, need_acc ? Acc : nullptr, rp, rp, rp, round, tol, n_rot);
-      TN_LAUNCHED();
+    if (geo.w > 0) {
+      const int nb = rp / geo.w;
+      for (int round = 0; round < nb - 1; ++round) {
+        jacobi_block_kernel<<<nb / 2, kBlkThreads, geo.smem, stream>>>(W, (int)ldw, len, need_acc ? Acc : nullptr, rp, geo.w, nb, round,
+                                                                       round == 0 ? 1 : 0, tol, n_rot);
+        TN_LAUNCHED();
+      }
+    } else {
+      for (int round = 0; round < rp - 1; ++round) {
+        jacobi_round_kernel<<<rp / 2, kJacThreads, 0, stream>>>(W, ldw, len, need_acc ? Acc : nullptr, rp, rp, rp, round, tol, n_rot);
+        TN_LAUNCHED();
+      }
     }
     unsigned h_rot = 0;
     TN_CUDA(cudaMemcpyAsync(&h_rot, n_rot, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));

@@ -253,9 +253,11 @@ class CudaBackend:
     # ---- a7/a11/a12: factorizations ----
     def svd(self, A, k_keep=None, precondition=True):
         """A (m,n) -> U (m,k), S (k), Vt (k,n) with the k largest singular triplets.
-        One-sided Jacobi (tn_svd_jacobi) on R^T of a QR factorisation of A (Drmac-Veselic preconditioning): the
-        triangular factor makes Jacobi converge in ~8 sweeps instead of 20-40 on ill-conditioned inputs and keeps the
-        small Schmidt values accurate to high relative precision; U = Q . U_R is one chain-GEMM call."""
+        One-sided Jacobi (tn_svd_jacobi) after two QR steps (Drmac-Veselic preconditioning):
+            A = Q1 R1,   R1^T = Q2 R2,   Jacobi on the columns of R2^T:  R2^T = Ux S Vx^T   =>   A = (Q1 Ux) S (Q2 Vx)^T.
+        The first triangular factor makes Jacobi converge in ~11 sweeps instead of 20-40 on graded Schmidt spectra, the
+        second one in ~8 (each QR costs about one sweep), and the small Schmidt values keep high relative accuracy.
+        U and Vt are one chain-GEMM call each."""
         A = A.contiguous()
         m, n = A.shape
         k = min(m, n) if k_keep is None else min(k_keep, m, n)
@@ -263,10 +265,18 @@ class CudaBackend:
             U2, S, Vt2 = self.svd(A.t().contiguous(), k_keep=k, precondition=precondition)
             return Vt2.t().contiguous(), S, U2.t().contiguous()
         if precondition and n > 1:
-            Q, R = self.qr(A)                               # (m,n), (n,n)
-            Ux, S, Vtx = self._jacobi(R.t().contiguous())   # R^T = Ux S Vtx  =>  A = (Q Vtx^T) S Ux^T
+            Q1, R1 = self.qr(A)                                  # (m,n), (n,n)
+            if n >= 64:
+                Q2, R2 = self.qr(R1.t().contiguous())            # (n,n), (n,n)
+                Ux, S, Vtx = self._jacobi(R2.t().contiguous(), k)   # (n,k), (k), (k,n)
+                U = self.empty(m, k)
+                self._gemm(0, m, k, n, Q1.contiguous(), Ux, n, k, U)            # U = Q1 Ux            (NN)
+                Vt = self.empty(k, n)
+                self._gemm(1, k, n, n, Vtx, Q2.contiguous(), n, n, Vt)          # Vt[j,i] = sum_l Vtx[j,l] Q2[i,l]   (NT)
+                return U, S, Vt
+            Ux, S, Vtx = self._jacobi(R1.t().contiguous())       # R1^T = Ux S Vtx  =>  A = (Q1 Vtx^T) S Ux^T
             U = self.empty(m, n)
-            self._gemm(1, m, n, n, Q.contiguous(), Vtx, n, n, U)   # U[i,j] = sum_l Q[i,l] Vtx[j,l]   (NT)
+            self._gemm(1, m, n, n, Q1.contiguous(), Vtx, n, n, U)   # U[i,j] = sum_l Q1[i,l] Vtx[j,l]   (NT)
             Vt = Ux.t().contiguous()
             if k < n:
                 U, S, Vt = U[:, :k].contiguous(), S[:k].contiguous(), Vt[:k].contiguous()

@@ -10,7 +10,10 @@ from tnalg_b200 import ops  # noqa: E402
 
 be = ops.backend()
 g = torch.Generator(device=be.device).manual_seed(0)
-for m, n in ((512, 256), (1024, 512), (2048, 1024)):
+SIZES = ((512, 256), (1024, 512), (2048, 1024), (512, 512), (1024, 1024), (2048, 2048))
+if len(sys.argv) > 2:
+    SIZES = ((int(sys.argv[1]), int(sys.argv[2])),)
+for m, n in SIZES:
     A = torch.randn(m, n, dtype=torch.float64, device=be.device, generator=g)
     # Schmidt-like graded spectrum
     U, S, Vt = torch.linalg.svd(A, full_matrices=False)
