@@ -31,6 +31,7 @@ WORKLOADS = {
     'heis_chain100_chi256': dict(kind='chain', l=100, chi=256),
     'xxz_chain200_chi512': dict(kind='chain', l=200, chi=512, jxy=1, jz=0.5, hx=0.3, hz=0),
     'j1j2_4x4_chi64': dict(kind='j1j2', w=4, h=4, chi=64),  # quick functional check
+    'heis_8x8_chi2048': dict(kind='j1j2', w=8, h=8, chi=2048, j2=0.0),  # BASELINE.json configs[4] (8 GPUs)
 }
 
 
@@ -45,15 +46,16 @@ def build_para(spec, chi=None):
         para = Pm.generate_parameters_dmrg('chain')
         para.update(spec)
         return Pm.make_consistent_parameter_dmrg(para)
-    w, h = spec.pop('w'), spec.pop('h')
+    w, h, j2 = spec.pop('w'), spec.pop('h'), spec.pop('j2', 0.5)
     nn = hm.positions_nearest_neighbor_square(w, h, 'open').astype(int)
     diag = []
     for r in range(h - 1):
         for c in range(w - 1):
-            diag.append([r * w + c, (r + 1) * w + c + 1])
-            diag.append([r * w + c + 1, (r + 1) * w + c])
-    pos = np.vstack([nn, np.array(diag, dtype=int)])
-    jj = np.concatenate([np.ones(nn.shape[0]), 0.5 * np.ones(len(diag))])
+            if j2 != 0.0:
+                diag.append([r * w + c, (r + 1) * w + c + 1])
+                diag.append([r * w + c + 1, (r + 1) * w + c])
+    pos = np.vstack([nn, np.array(diag, dtype=int).reshape(-1, 2)])
+    jj = np.concatenate([np.ones(nn.shape[0]), j2 * np.ones(len(diag))])
     para = dict(Pm.common_parameters_dmrg())
     op = hm.spin_operators('half')
     L = w * h
