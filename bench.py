@@ -75,6 +75,7 @@ def _json_default(o):
 
 
 def bond_dims(L, d, chi):
+    L, d, chi = int(L), int(d), int(chi)   # python ints: d ** L overflows int64 at L = 64
     return [min(d ** n, chi, d ** (L - n)) for n in range(L + 1)]
 
 
@@ -86,7 +87,7 @@ def site_counts(para):
     out = []
     for p in range(para['l']):
         kl, kr, nx = t.counts(p)
-        a, b, d = dims[p], dims[p + 1], para['d']
+        a, b, d = dims[p], dims[p + 1], int(para['d'])
         out.append(dict(site=p, a=a, b=b, kl=kl, kr=kr, nx=nx, flop=2.0 * a * d * b * (a * (kl + nx) + b * (kr + nx))))
     return out
 
@@ -391,9 +392,9 @@ def run_ours(args, para, workload):
         'roofline': {'bound': 'tensor', 'kernel': 'chain_gemm_tma_kernel (left + right stage launches of one matvec at the widest site)',
                      'achieved': executed_tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': executed_tf / peak, 'traffic': traffic,
                      'flop_per_matvec_executed': executed_flop, 'flop_per_matvec_reference_grouping': widest['flop'],
-                     'achieved_reference_grouping': achieved, 'tma_stages': uses_tma,
+                     'achieved_reference_grouping': achieved, 'tma_stage_mask': uses_tma,
                      'note': 'achieved = flop the two launches execute / CUDA-event time. Crossing terms that share an operator are summed '
-                             'before the GEMM (same H_eff, n_x 42 -> 15 links at this site), so the kernels execute fewer flop than the '
+                             'before the GEMM (same H_eff; e.g. n_x 42 -> 15 links at the widest 6x6 J1-J2 site), so the kernels execute fewer flop than the '
                              'reference grouping of SURVEY 8d (K_L, K_R, n_x); counted in reference-grouping flop the same matvec runs at '
                              'achieved_reference_grouping TFLOP/s, which may exceed the hardware peak',
                      'peak_source': 'cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry); '
