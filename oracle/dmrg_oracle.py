@@ -105,7 +105,7 @@ def make_para(lattice='chain', **kw):
         para.setdefault('op', ops + [np.zeros((d, d))])
     else:
         raise ValueError(lattice)
-    para['d'] = d
+    para['d'] = int(np.asarray(para['op'][0]).shape[0])   # user-supplied operators decide ('arbitrary' with spin-1 ops)
     para['nh'] = para['index2'].shape[0]
     return para
 

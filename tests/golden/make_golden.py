@@ -8,6 +8,7 @@ nothing here is computed by the oracle or by the CUDA path.
 Cases
   e2e_chain12      BASELINE cfg1: Heisenberg open chain N=12 chi=16, tight tolerances, seed 0
   e2e_xxz10        XXZ (jxy=1,jz=0.5) + hx=0.3 chain N=10 chi=12 (one-body terms, '0_s_0' group)
+  e2e_spin1_chain8 spin-1 Heisenberg open chain N=8 chi=12 (d = 3 path, Parameters.py:440-446), seed 3
   e2e_j1j2_4x2     J1-J2 4x2 'arbitrary' lattice chi=16 = exact (crossing '1_0_1' terms; even site count so
                    the ground state is a unique singlet -- 3x3 has a degenerate doublet)
   percall_j1j2     one MPS snapshot + per-call reference outputs: matvec handle, dense H_eff, opt_env key
@@ -221,12 +222,16 @@ def main():
         'e2e_chain12': lambda: pack_run(chain_para(l=12, chi=16, **TIGHT), 0),
         'e2e_xxz10': lambda: pack_run(chain_para(l=10, chi=12, jxy=1, jz=0.5, hx=0.3, hz=0, **TIGHT), 1),
         'e2e_j1j2_4x2': lambda: pack_run(j1j2_para(4, 2, 16, **TIGHT), 2),
+        'e2e_spin1_chain8': lambda: pack_run(chain_para(l=8, chi=12, spin=sys.intern('one'), **TIGHT), 3),
         'percall_j1j2': percall_case,
         'pr_fixtures': pr_fixtures,
         'docstring_kats': docstring_kats,
         'truncation_lib': truncation_case,
     }
+    only = sys.argv[1:]
     for name, fn in cases.items():
+        if only and name not in only:
+            continue
         data = fn()
         path = os.path.join(HERE, name + '.npz')
         np.savez_compressed(path, **data)

@@ -9,7 +9,7 @@ def para_from_golden(g, **kw):
     from tnalg_b200 import Parameters as Pm
     para = dict(Pm.common_parameters_dmrg())
     ops = [np.real(o) if np.abs(np.imag(o)).max() == 0 else o for o in g['op']]
-    para.update(lattice='arbitrary', spin='half', op=ops, index1=g['index1'], coeff1=g['coeff1'], index2=g['index2'],
+    para.update(lattice='arbitrary', spin='one' if int(g['d']) == 3 else 'half', op=ops, index1=g['index1'], coeff1=g['coeff1'], index2=g['index2'],
                 coeff2=g['coeff2'], chi=int(g['chi']), tau=float(g['tau']), eigs_tol=float(g['eigs_tol']),
                 break_tol=float(g['break_tol']), hx=float(g['hx']), hz=float(g['hz']))
     para.update(kw)
@@ -55,7 +55,7 @@ def test_observables_on_reference_snapshot(golden):
         assert np.abs(A.observe_magnetization(3) - g['ob_mz']).max() < 1e-11
 
 
-@pytest.mark.parametrize('case', ['e2e_chain12', 'e2e_xxz10', 'e2e_j1j2_4x2'])
+@pytest.mark.parametrize('case', ['e2e_chain12', 'e2e_xxz10', 'e2e_j1j2_4x2', 'e2e_spin1_chain8'])
 def test_end_to_end_vs_reference(golden, case):
     """converged, tight-tolerance runs: sweep energies and truncated spectrum rel 1e-10, observables abs 1e-8"""
     from tnalg_b200.DMRG_anyH import dmrg_finite_size

@@ -24,7 +24,7 @@ def para_from_golden(g, **kw):
     from tnalg_b200 import Parameters as Pm
     para = dict(Pm.common_parameters_dmrg())
     ops = [np.real(o) if np.abs(np.imag(o)).max() == 0 else o for o in g['op']]
-    para.update(lattice='arbitrary', spin='half', op=ops, index1=g['index1'], coeff1=g['coeff1'], index2=g['index2'],
+    para.update(lattice='arbitrary', spin='one' if int(g['d']) == 3 else 'half', op=ops, index1=g['index1'], coeff1=g['coeff1'], index2=g['index2'],
                 coeff2=g['coeff2'], chi=int(g['chi']), tau=float(g['tau']), eigs_tol=float(g['eigs_tol']),
                 break_tol=float(g['break_tol']), hx=float(g['hx']), hz=float(g['hz']))
     para.update(kw)
@@ -100,7 +100,7 @@ def test_observables_vs_reference(golden, cpu_be):
         assert np.abs(A.observe_bond_energy(g['index2'], g['coeff2']) - g['ob_eb_full']).max() < 1e-12
 
 
-@pytest.mark.parametrize('case', ['e2e_chain12', 'e2e_xxz10', 'e2e_j1j2_4x2'])
+@pytest.mark.parametrize('case', ['e2e_chain12', 'e2e_xxz10', 'e2e_j1j2_4x2', 'e2e_spin1_chain8'])
 def test_end_to_end_vs_reference(golden, cpu_be, case):
     """dmrg_finite_size through the product's host code: converged energies / spectrum rel 1e-10, observables 1e-8"""
     from tnalg_b200.DMRG_anyH import dmrg_finite_size
