@@ -342,6 +342,40 @@ def test_svd_rank_deficient_two_site_wavefunction(be):
     assert np.abs((U * S) @ Vt - A).max() < 1e-13
 
 
+@pytest.mark.parametrize('n', [256, 512])
+def test_svd_spectrum_decaying_through_roundoff_converges(be, n):
+    """two-site wavefunction late in a sweep: singular values decay smoothly from 1 to 1e-22, a third of them below the
+    round-off level of the matrix; the truncating call must converge (regression: a shortcut that skipped pairs of
+    negligible rows stalled the blocked kernels on such inputs) and keep the leading values exact"""
+    rng = np.random.RandomState(n)
+    s = np.logspace(0, -22, n)
+    A = (np.linalg.qr(rng.randn(n, n))[0] * s) @ np.linalg.qr(rng.randn(n, n))[0].T
+    U, S, Vt = [be.to_numpy(x) for x in be.svd(be.from_numpy(A), k_keep=n // 2)]
+    assert be.last_svd_sweeps <= 40
+    lead = s > 1e-9
+    assert np.abs(S[lead[:n // 2]] / s[:n // 2][lead[:n // 2]] - 1).max() < 1e-6
+    assert np.abs(U.T @ U - np.eye(n // 2)).max() < 1e-12 and np.abs(Vt @ Vt.T - np.eye(n // 2)).max() < 1e-12
+
+
+@pytest.mark.parametrize('k_keep', [30, 60, 96])
+def test_svd_truncation_beyond_numerical_rank_stays_orthonormal(be, k_keep):
+    """rank 40 matrix (the rest is exactly at round-off level): asking for fewer, more, or all triplets must give orthonormal
+    vectors -- pairs of negligible rows are only skipped when enough rows stay above the round-off level"""
+    rng = np.random.RandomState(21)
+    n, r = 96, 40
+    A = (np.linalg.qr(rng.randn(n, r))[0] * np.logspace(0, -6, r)) @ np.linalg.qr(rng.randn(n, r))[0].T
+    for precondition in (True, False):
+        U, S, Vt = [be.to_numpy(x) for x in be.svd(be.from_numpy(A), k_keep=k_keep, precondition=precondition)]
+        assert U.shape == (n, k_keep) and Vt.shape == (k_keep, n)
+        kk = min(k_keep, r)
+        assert np.abs(S[:kk] / np.logspace(0, -6, r)[:kk] - 1).max() < 1e-9
+        assert np.abs(U[:, :kk].T @ U[:, :kk] - np.eye(kk)).max() < 1e-12
+        assert np.abs(Vt[:kk] @ Vt[:kk].T - np.eye(kk)).max() < 1e-12
+        assert np.abs(Vt @ Vt.T - np.eye(k_keep)).max() < 1e-10     # accumulated rotations: orthonormal for every row
+        u0, s0, v0 = np.linalg.svd(A)
+        assert np.abs((U[:, :kk] * S[:kk]) @ Vt[:kk] - (u0[:, :kk] * s0[:kk]) @ v0[:kk]).max() < 1e-13
+
+
 def test_svd_matches_cusolver_baseline(be):
     """cuSOLVER (torch.linalg.svd) is kept only as a checked baseline (north_star)"""
     import torch

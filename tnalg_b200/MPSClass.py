@@ -359,6 +359,10 @@ class MpsOpenBoundaryClass(MpsBasic):
             raise RuntimeError('CenterError: central-orthogonalize MPS before updating the tensor')
         if not 0 <= p < self.length - 1:
             raise ValueError('two-site update needs 0 <= p < length-1')
+        from ._lib import MAX_D
+        if self.phys_dim ** 2 > MAX_D and type(be).__name__ == 'CudaBackend':
+            raise NotImplementedError('two-site update: combined physical dimension d*d = %d exceeds TN_MAX_PHYS_DIM = %d '
+                                      '(spin-1/2 only; use the one-site sweep for spin-1)' % (self.phys_dim ** 2, MAX_D))
         self.correct_orthogonal_center(p)
         env = self._environments(index1, index2, coeff1, coeff2, tol)
         dist = self._dist()

@@ -37,7 +37,24 @@ struct tn_effh_plan {
   // TMA staging (chain_gemm_tma.cu): tensor maps of the fixed operands; psi maps are encoded per call
   bool tmaA, tmaB;
   TmaMap* maps;
+  // small plans without crossing terms: the two stages are independent and latency bound, so they run concurrently
+  bool overlapAB;
 };
+
+// side stream + events for the concurrent stages (one device per process)
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideStream* side_stream() {
+  static SideStream x;
+  if (!x.s) {
+    if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return &x;
+}
 
 static bool owns(int idx, int rank, int world) { return world <= 1 || idx % world == rank; }
 
@@ -139,6 +156,11 @@ extern "C" int tn_effh_plan_create(tn_effh_plan** out_plan, int a, int d, int b,
   P->n_phi = n_phi;
   P->haveA = !pa.empty();
   P->haveB = !lb.empty();
+  // independent stages (no crossing term feeds the right stage) of a small site: both add into `out` with atomics and run
+  // on two streams (chi = 256 chain: 2 x 22 us of latency-bound launches per matvec overlap)
+  P->overlapAB = P->haveA && P->haveB && n_phi == 0 && (long long)a * d * b <= (1LL << 19) && !getenv("TNALG_NO_OVERLAP");
+  if (P->overlapAB)
+    for (auto& q : pa) q.shared_out = 1;
   const double* fake_psi = reinterpret_cast<const double*>(uintptr_t(256));  // alignment stand-in for scheduling
   const bool use_tma = tma_available() && !getenv("TNALG_NO_TMA");
   std::vector<TmaMap> hmaps;
@@ -182,7 +204,7 @@ extern "C" int tn_effh_plan_create(tn_effh_plan** out_plan, int a, int d, int b,
     for (int l0 = 0; l0 < nl; l0 += kChunk) {
       ProblemDev q{};
       q.C = nullptr; q.alpha = 1.0; q.link_begin = l0; q.link_count = std::min(kChunk, nl - l0); q.accumulate = 1; q.c_dyn = 1;
-      q.shared_out = nl > kChunk ? 1 : 0;
+      q.shared_out = (nl > kChunk || P->overlapAB) ? 1 : 0;
       pb.push_back(q);
     }
     P->LB = GemmLaunch{TN_NT, a * d, b, b, d, b, b, b, (int)pb.size(), nl, 0};
@@ -226,6 +248,20 @@ extern "C" int tn_effh_matvec(tn_effh_plan* P, const double* psi_in, double* psi
   TmaMap psi_a, psi_b;  // psi as the A operand of the right stage / the (k, s, y) B operand of the left stage
   if (P->tmaA) TN_CHECK(tma_encode_3d(&psi_b, psi_in, P->a, P->d, P->b, (long long)P->d * P->b));
   if (P->tmaB) TN_CHECK(tma_encode_2d(&psi_a, psi_in, (long long)P->a * P->d, P->b, P->b, tma_box_rows_a()));
+  SideStream* side = P->overlapAB ? side_stream() : nullptr;
+  cudaStream_t streamB = stream;
+  if (side) {  // fork: the right stage runs on the side stream after the init kernel
+    TN_CUDA(cudaEventRecord(side->fork, stream));
+    TN_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
+    streamB = side->s;
+  }
+  if (side && P->haveB) {
+    if (P->tmaB)
+      TN_CHECK(gemm_launch_tma(P->LB, P->SB, P->probB, P->linkB, P->maps, psi_a, psi_b, psi_in, psi_out, c_h, streamB));
+    else
+      TN_CHECK(gemm_launch(P->LB, P->SB, P->probB, P->linkB, psi_in, psi_out, c_h, streamB));
+    TN_CUDA(cudaEventRecord(side->join, streamB));
+  }
   if (P->haveA) {
     if (P->SA.split && P->n_phi > 0) TN_CUDA(cudaMemsetAsync(P->phi, 0, sizeof(double) * (size_t)P->n * P->n_phi, stream));
     if (P->tmaA)
@@ -233,7 +269,9 @@ extern "C" int tn_effh_matvec(tn_effh_plan* P, const double* psi_in, double* psi
     else
       TN_CHECK(gemm_launch(P->LA, P->SA, P->probA, P->linkA, psi_in, psi_out, c_h, stream));
   }
-  if (P->haveB) {
+  if (side) {
+    TN_CUDA(cudaStreamWaitEvent(stream, side->join, 0));  // join
+  } else if (P->haveB) {
     if (P->tmaB)
       TN_CHECK(gemm_launch_tma(P->LB, P->SB, P->probB, P->linkB, P->maps, psi_a, psi_b, psi_in, psi_out, c_h, stream));
     else
