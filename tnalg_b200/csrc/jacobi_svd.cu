@@ -264,7 +264,8 @@ __global__ void __launch_bounds__(kBlkThreads, 1) jacobi_block_kernel(double* __
 // a rotation is thread-local and needs no data movement at all; only the 3W dot products of a round are reduced across the
 // CTA (packed reduce-scatter with warp shuffles, 9 shuffles per 2 pairs, then one shared-memory hop across the 16 warps).
 // The pair schedule is unrolled at compile time so that every register index is static.  W x C = 16: (16,1) rows up to 512
-// doubles (work row + accumulator row), (8,2) up to 1024, (4,4) up to 2048.
+// doubles (work row + accumulator row), (8,2) up to 1024, (4,4) up to 2048.  Only (8,2) and (4,4) are instantiated: rows of at
+// most 512 doubles run faster on the shared-memory kernel with w = 16.
 constexpr int kRegThreads = 512;
 constexpr int kRegWarps = kRegThreads / 32;
 
@@ -612,8 +613,7 @@ extern "C" int tn_svd_jacobi(const double* A, int m, int n, int k_keep, double* 
 #define TN_JREG(WW, CC)                                                                                                              \
   if (full) jacobi_block_reg_kernel<WW, CC, true><<<nb / 2, kRegThreads, 0, stream>>>(W, (int)ldw, acc, rp, nb, round, tol, n_rot); \
   else jacobi_block_reg_kernel<WW, CC, false><<<nb / 2, kRegThreads, 0, stream>>>(W, (int)ldw, acc, rp, nb, round, tol, n_rot)
-          if (geo.w == 16) { TN_JREG(16, 1); }
-          else if (geo.w == 8) { TN_JREG(8, 2); }
+          if (geo.w == 8) { TN_JREG(8, 2); }
           else { TN_JREG(4, 4); }
 #undef TN_JREG
           TN_LAUNCHED();
