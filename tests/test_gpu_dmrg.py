@@ -137,3 +137,57 @@ def test_truncate_virtual_bonds_vs_oracle():
     """a12 on the device: Jacobi SVD with k_keep as the truncating gauge move"""
     from tests.test_host_logic_cpu import _check_truncation
     _check_truncation()
+
+
+def _full_size_checks(chi, n_ranks):
+    """size-independent properties on the bench workload (6x6 J1-J2): see test_full_size_properties_chi1024"""
+    import bench
+    from tnalg_b200 import ops
+    from tnalg_b200.MPSClass import MpsOpenBoundaryClass
+    be = ops.backend()
+    para = bench.build_para(bench.WORKLOADS['j1j2_6x6_chi1024'], chi)
+    L, d = para['l'], para['d']
+    args = (para['index1'], para['index2'], para['coeff1'], para['coeff2'])
+    np.random.seed(8)
+    A = MpsOpenBoundaryClass(L, d, para['chi'], operators=para['op'], is_save_op=True, eig_way=1)
+    p = L // 2 - 1 if chi < 64 else 11                                   # widest site of the bench (a = b = chi)
+    A.correct_orthogonal_center(p)
+    A.mps[p] = A.mps[p] / A.norm_mps()                                    # random tensors: normalise the centre
+    assert abs(A.norm_mps() - 1) < 1e-12
+    plan = A.effective_hamiltonian_plan(p, *args, tol=para['eigs_tol'])
+    psi = A.mps[p]
+    rng = np.random.RandomState(1)
+    x, y = be.from_numpy(rng.randn(*psi.shape)), be.from_numpy(rng.randn(*psi.shape))
+    hx, hy = plan.matvec(x).clone(), plan.matvec(y).clone()
+    # (1) symmetry and (2) linearity of the matvec
+    xhy, yhx = float((x * hy).sum()), float((y * hx).sum())
+    assert abs(xhy - yhx) < 1e-11 * float(hx.norm()) * float(y.norm())
+    hz = plan.matvec(0.3 * x - 1.7 * y)
+    assert float((hz - (0.3 * hx - 1.7 * hy)).norm()) < 1e-12 * float(hx.norm() + hy.norm())
+    # (3) term-sharded plans add up to the full operator (the multi-GPU decomposition, without a collective)
+    parts = None
+    for r in range(n_ranks):
+        pr = A._environments(*args, para['eigs_tol']).plan(p, A.mps, rank=r, world=n_ranks)
+        out = pr.matvec(x).clone()
+        parts = out if parts is None else parts + out
+        pr.destroy()
+    assert float((parts - hx).norm()) < 1e-12 * float(hx.norm())
+    # (4) checksum of checksums: <psi|H_eff|psi> through the matvec kernels == sum of all bond energies through the
+    #     observable path (independent code: expect_products / tn_env_update chains / tn_trace)
+    e_plan = float((psi * plan.matvec(psi)).sum())
+    e_obs = float(np.sum(A.observe_bond_energy(para['index2'], para['coeff2'])))
+    assert abs(e_plan - e_obs) < 1e-10 * max(1.0, abs(e_obs)), (e_plan, e_obs)
+    # (5) one local solve is variational and leaves a normalised, gauge-consistent state
+    A.update_tensor_eigs(p, *args, para['tau'], para['is_real'], tol=para['eigs_tol'])
+    assert abs(A.norm_mps() - 1) < 1e-12
+    e_after = float(np.sum(A.observe_bond_energy(para['index2'], para['coeff2'])))
+    assert e_after <= e_obs + 1e-9 * abs(e_obs)
+    assert A.last_eig['converged'] and abs((1.0 - A.last_eig['lambda']) / para['tau'] - e_after) < 1e-6 * abs(e_after)
+    plan.destroy()
+
+
+def test_full_size_properties_chi1024():
+    """BASELINE.json's full size (6x6 J1-J2, chi = 1024, a = b = 1024 at the probed site): far beyond what the oracle can run,
+    so parity is anchored on properties: symmetry, linearity, shard additivity, the energy of the state computed by the
+    matvec path against the same energy from the observable path, and a variational local update"""
+    _full_size_checks(1024, 4)
