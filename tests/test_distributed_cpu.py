@@ -70,6 +70,64 @@ def test_two_ranks_two_site_sweep_agree_with_exact_energy():
     assert abs(e0 * para['l'] - exact) < 1e-10 * abs(exact) and max(vd0) == 16
 
 
+def _scan_paras(tmp):
+    """a small (hx) scan of a transverse-field Ising chain, like ScriptRun/DMRG/runDMRGfull.py:27-39"""
+    from tnalg_b200 import Parameters as Pm
+    out = []
+    for hx in (0.2, 0.5, 0.8, 1.1, 1.4):
+        para = Pm.generate_parameters_dmrg('chain')
+        para.update(l=6, chi=8, jxy=0, jz=1, hx=hx, hz=0, eigs_tol=1e-12, break_tol=1e-13, data_path=tmp)
+        out.append(Pm.make_consistent_parameter_dmrg(para))
+    return out
+
+
+def _worker_scan(rank, world, port, tmp, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from tests.cpu_backend import CpuBackend
+        from tnalg_b200 import ops
+        from tnalg_b200.DMRG_anyH import run_parameter_scan
+        ops.set_backend(CpuBackend())
+        q.put((rank, run_parameter_scan(_scan_paras(tmp), save=True, seed=7)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_parameter_scan_is_distributed_over_ranks_without_term_sharding(tmp_path):
+    """independent runs (weak scaling, no data-path collective): every rank reports all runs, energies equal ED, each run
+    left its .pr file, and the result equals the serial loop"""
+    from oracle import dmrg_oracle as orc
+    from tests.cpu_backend import CpuBackend
+    from tnalg_b200 import BasicFunctionsSJR as bf, ops
+    from tnalg_b200.DMRG_anyH import run_parameter_scan
+    world, port = 2, 33500 + os.getpid() % 2000
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_scan, args=(r, world, port, str(tmp_path), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0] == res[1] and [r[0] for r in res[0]] == [0, 1, 2, 3, 4]
+    paras = _scan_paras(str(tmp_path))
+    for (n, e, n_sweeps, conv), para in zip(res[0], paras):
+        e0 = np.linalg.eigvalsh(orc.dense_hamiltonian(para))[0]
+        assert abs(e * para['l'] - e0) < 1e-10 * abs(e0)
+        saved = bf.load_pr(os.path.join(str(tmp_path), para['data_exp'] + '.pr'))
+        assert abs(float(np.ravel(saved['ob']['e_per_site'])[0]) - e) == 0 and saved['A'].length == para['l']
+    old = ops._backend
+    ops.set_backend(CpuBackend())
+    try:
+        serial = run_parameter_scan(paras, save=False, seed=7)
+    finally:
+        ops.set_backend(old)
+    assert [r[:2] for r in serial] == [r[:2] for r in res[0]]
+
+
 @pytest.mark.parametrize('case', ['e2e_j1j2_4x2'])
 def test_two_ranks_shard_terms_and_agree(case):
     world, port = 2, 29500 + os.getpid() % 2000

@@ -42,6 +42,7 @@ def dmrg_finite_size(para=None, quiet=True):
     A = Mob(length=para['l'], d=para['d'], chi=para['chi'], way='qr', ini_way='r', operators=para['op'], debug=is_debug,
             is_parallel=para['isParallel'], par_pool=None, is_save_op=para['is_save_op'], eig_way=para['eigWay'],
             is_env_parallel_lmr=para['isParallelEnvLMR'])
+    A.shard_terms = bool(para.get('shard_terms', True))   # False: independent runs per rank (parameter scans)
     A.correct_orthogonal_center(para['ob_position'])
     e0_per_site = 0
     info['convergence'] = 1
@@ -55,12 +56,12 @@ def dmrg_finite_size(para=None, quiet=True):
             observe(A, para, ob)
             info['convergence'] = abs(ob['e_per_site'] - e0_per_site)
             if info['convergence'] < para['break_tol']:
-                say('Converged at the %d-th sweep with error = %g of energy per site.' % (t + 1, info['convergence']))
+                say('Converged at the %d-th sweep with error = %g of energy per site.' % (t + 1, np.ravel(info['convergence'])[0]))
                 break
-            say('Convergence error of energy per site = %g' % info['convergence'])
+            say('Convergence error of energy per site = %g' % np.ravel(info['convergence'])[0])
             e0_per_site = ob['e_per_site']
         if t == para['sweep_time'] - 1 and info['convergence'] > para['break_tol']:
-            say('Not converged with error = %g of eb per bond' % info['convergence'])
+            say('Not converged with error = %g of eb per bond' % np.ravel(info['convergence'])[0])
     ob['eb'] = get_bond_energies(ob['eb_full'], para['positions_h2'], para['index2'])
     A.calculate_entanglement_spectrum()
     A.calculate_entanglement_entropy()
@@ -97,6 +98,7 @@ def dmrg_finite_size_two_site(para=None, chi_init=None, quiet=True):
     A = Mob(length=para['l'], d=para['d'], chi=chi0, way='qr', ini_way='r', operators=para['op'], debug=is_debug,
             is_parallel=para['isParallel'], par_pool=None, is_save_op=para['is_save_op'], eig_way=para['eigWay'],
             is_env_parallel_lmr=para['isParallelEnvLMR'])
+    A.shard_terms = bool(para.get('shard_terms', True))
     A.correct_orthogonal_center(0)
     info = {'convergence': 1, 'n_sweeps': 0}
     ob, e0 = dict(), 0
@@ -120,6 +122,39 @@ def dmrg_finite_size_two_site(para=None, chi_init=None, quiet=True):
     info.update({k: A.stats[k] for k in ('n_solves', 'n_matvec', 'flops_algorithmic', 'flops_executed', 'not_converged')})
     A.clean_to_save()
     return ob, A, info, para
+
+
+def run_parameter_scan(paras, save=True, seed=None, two_site=False):
+    """Independent DMRG runs over a list of para dicts, distributed over the ranks of torch.distributed (run n goes to rank
+    n mod world; no collective on the data path -- the pattern of the reference's ScriptRun/DMRG/runDMRGfull.py:27-39, 110
+    runs over a (theta, alpha) grid, each saved as data_path/data_exp.pr).  Every rank returns the list of
+    (index, e_per_site, n_sweeps, convergence) of ALL runs (gathered with all_gather_object); the .pr files are written by
+    the rank that owns the run.  Without an initialised process group it is a plain serial loop."""
+    import numpy as np
+    from . import BasicFunctionsSJR as bf
+    try:
+        import torch.distributed as dist
+        on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    except Exception:  # pragma: no cover
+        dist, on = None, False
+    rank, world = (dist.get_rank(), dist.get_world_size()) if on else (0, 1)
+    mine = []
+    for n, para in enumerate(paras):
+        if n % world != rank:
+            continue
+        para = dict(para)
+        para['shard_terms'] = False                      # this rank owns the whole run
+        if seed is not None:
+            np.random.seed(seed + n)
+        ob, A, info, para = (dmrg_finite_size_two_site if two_site else dmrg_finite_size)(para)
+        if save:
+            bf.save_pr(para.get('data_path', './data_dmrg'), para['data_exp'] + '.pr', (ob, A, info, para), ('ob', 'A', 'info', 'para'))
+        mine.append((n, float(np.ravel(ob['e_per_site'])[0]), int(info.get('n_sweeps', 0)), float(np.ravel(info['convergence'])[0])))
+    if not on:
+        return mine
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine)
+    return sorted(r for part in everyone for r in part)
 
 
 def get_bond_energies(eb_full, positions, index2):
