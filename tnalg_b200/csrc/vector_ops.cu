@@ -73,7 +73,30 @@ __global__ void __launch_bounds__(kDotThreads) multidot_kernel(const double* __r
   const long long e0 = (long long)chunk * kDotChunk;
   const long long e1 = min(e0 + kDotChunk, n);
   double acc = 0.0;
-  for (long long e = e0 + threadIdx.x; e < e1; e += kDotThreads) acc += v[e] * w[e];
+  if ((((uintptr_t)(v + e0) | (uintptr_t)(w + e0)) & 15) == 0) {
+    // 16-byte loads, four independent pairs in flight per thread (HBM-bound: bytes in flight are what matters)
+    const double2* v2 = reinterpret_cast<const double2*>(v + e0);
+    const double2* w2 = reinterpret_cast<const double2*>(w + e0);
+    const int n2 = (int)((e1 - e0) >> 1);
+    double acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    int e = threadIdx.x;
+    for (; e + 3 * kDotThreads < n2; e += 4 * kDotThreads) {
+      const double2 a0 = v2[e], a1 = v2[e + kDotThreads], a2 = v2[e + 2 * kDotThreads], a3 = v2[e + 3 * kDotThreads];
+      const double2 b0 = w2[e], b1 = w2[e + kDotThreads], b2 = w2[e + 2 * kDotThreads], b3 = w2[e + 3 * kDotThreads];
+      acc += a0.x * b0.x + a0.y * b0.y;
+      acc1 += a1.x * b1.x + a1.y * b1.y;
+      acc2 += a2.x * b2.x + a2.y * b2.y;
+      acc3 += a3.x * b3.x + a3.y * b3.y;
+    }
+    for (; e < n2; e += kDotThreads) {
+      const double2 a0 = v2[e], b0 = w2[e];
+      acc += a0.x * b0.x + a0.y * b0.y;
+    }
+    acc = (acc + acc1) + (acc2 + acc3);
+    if (((e1 - e0) & 1) && threadIdx.x == 0) acc += v[e1 - 1] * w[e1 - 1];
+  } else {
+    for (long long e = e0 + threadIdx.x; e < e1; e += kDotThreads) acc += v[e] * w[e];
+  }
   acc = warp_sum(acc);
   __shared__ double s_part[kDotThreads / 32];
   __shared__ bool s_last;
@@ -91,11 +114,16 @@ __global__ void __launch_bounds__(kDotThreads) multidot_kernel(const double* __r
   __syncthreads();
   if (s_last) {
     __threadfence();
-    for (int i = threadIdx.x; i < (int)gridDim.y; i += kDotThreads) {
-      double s = 0.0;
+    // one warp per vector: lanes take the chunk partials strided (loads in flight instead of a serial chain of 256
+    // dependent L2 reads), then a fixed shuffle tree -- the summation order depends only on (chunks), so the result stays
+    // bit-reproducible
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = warp; i < (int)gridDim.y; i += kDotThreads / 32) {
       const volatile double* pp = partial + (long long)i * chunks;
-      for (int c = 0; c < chunks; ++c) s += pp[c];
-      result[i] = s;
+      double s = 0.0;
+      for (int c = lane; c < chunks; c += 32) s += pp[c];
+      s = warp_sum(s);
+      if (lane == 0) result[i] = s;
     }
     if (threadIdx.x == 0) *counter = 0u;
   }
