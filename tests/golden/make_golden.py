@@ -217,6 +217,24 @@ def truncation_case():
     return out
 
 
+def rdm_case():
+    """two-body reduced density matrices of a converged reference state (MPSClass.py:841-855), centre left of, between and
+    right of the pair; XXZ + field chain N=8, chi=16 (exact), seed 4."""
+    para = chain_para(l=8, chi=16, jxy=1, jz=0.7, hx=0.4, hz=0.15, **TIGHT)
+    ob, A, info, para = ref_shim.run_finite_dmrg(dict(para), 4)
+    out = {'seed': 4, 'l': para['l'], 'chi': para['chi'], 'd': para['d'], 'tau': para['tau'], 'eigs_tol': para['eigs_tol'],
+           'break_tol': para['break_tol'], 'hx': para['hx'], 'hz': para['hz'], 'index1': np.asarray(para['index1']),
+           'index2': np.asarray(para['index2']), 'coeff1': np.asarray(para['coeff1']), 'coeff2': np.asarray(para['coeff2']),
+           'op': np.stack([np.asarray(o, dtype=complex) for o in para['op']]), 'e_per_site': ob['e_per_site']}
+    pairs = [(3, 4), (1, 6), (0, 7), (2, 3), (5, 7)]
+    out['pairs'] = np.array(pairs)
+    for c in (0, 4, 7):
+        A.correct_orthogonal_center(c)
+        for p1, p2 in pairs:
+            out['rdm_c%d_%d_%d' % (c, p1, p2)] = A.reduced_density_matrix_two_body(p1, p2)
+    return out
+
+
 def main():
     cases = {
         'e2e_chain12': lambda: pack_run(chain_para(l=12, chi=16, **TIGHT), 0),
@@ -227,6 +245,7 @@ def main():
         'pr_fixtures': pr_fixtures,
         'docstring_kats': docstring_kats,
         'truncation_lib': truncation_case,
+        'rdm_xxz8': rdm_case,
     }
     only = sys.argv[1:]
     for name, fn in cases.items():

@@ -191,3 +191,11 @@ def test_full_size_properties_chi1024():
     so parity is anchored on properties: symmetry, linearity, shard additivity, the energy of the state computed by the
     matvec path against the same energy from the observable path, and a variational local update"""
     _full_size_checks(1024, 4)
+
+
+def test_rdm_full_state_dense_heff_and_checks(golden):
+    """a10 reduced_density_matrix_two_body (vs the unmodified reference), full_coefficients_mps, a9 dense H_eff through the
+    matvec plan (vs the oracle) and the check_* helpers on the CUDA backend"""
+    from tests.test_host_logic_cpu import check_rdm_and_dense_helpers
+    from tnalg_b200 import ops
+    check_rdm_and_dense_helpers(golden, ops.backend())

@@ -237,3 +237,52 @@ def _check_truncation():
     B.correct_orthogonal_center(0)
     B.truncate_virtual_bonds(chi1, center=3, way='simple')
     assert max(B.virtual_dim) <= chi1 and B.center == 3 and abs(B.norm_mps() - 1) < 1e-12
+
+
+def _converged_state_for_rdm(golden):
+    from tnalg_b200 import DMRG_anyH
+    g = golden('rdm_xxz8')
+    para = para_from_golden(g)
+    np.random.seed(int(g['seed']))
+    ob, A, info, para = DMRG_anyH.dmrg_finite_size(para)
+    return g, para, ob, A
+
+
+def check_rdm_and_dense_helpers(golden, be):
+    """reduced_density_matrix_two_body vs the unmodified reference (MPSClass.py:841-855) for centres left of / inside /
+    right of the pair, vs the partial trace of full_coefficients_mps; effective_hamiltonian_dmrg vs the oracle's dense
+    H_eff; the check_* helpers.  Shared by the CPU (stand-in backend) and GPU tests."""
+    from oracle import dmrg_oracle as orc
+    g, para, ob, A = _converged_state_for_rdm(golden)
+    assert abs(float(np.ravel(ob['e_per_site'])[0]) - float(g['e_per_site'][0])) <= 1e-10 * abs(float(g['e_per_site'][0]))
+    A.mps = [be.from_numpy(np.asarray(t)) for t in A.mps]       # back on the device after clean_to_save
+    L, d = para['l'], para['d']
+    psi = None
+    for c in (0, 4, 7):
+        A.correct_orthogonal_center(c)
+        assert A.check_orthogonality_by_tensors(is_print=False) == [] and A.check_virtual_bond_dimensions() == []
+        assert abs(A.check_mps_norm1() - 1) < 1e-12
+        if psi is None:
+            psi = A.full_coefficients_mps().reshape([d] * L)
+            assert abs(np.linalg.norm(psi) - 1) < 1e-12
+        for p1, p2 in g['pairs']:
+            rho = A.reduced_density_matrix_two_body(int(p1), int(p2))
+            assert np.abs(rho - g['rdm_c%d_%d_%d' % (c, p1, p2)]).max() < 1e-8          # reference, observables tolerance
+            keep = [int(p1), int(p2)]
+            rest = [n for n in range(L) if n not in keep]
+            m = psi.transpose(keep + rest).reshape(d * d, -1)
+            assert np.abs(rho - m @ m.T).max() < 1e-12                                  # partial trace of the full state
+    # dense H_eff through the plan == oracle's kron-built dense H_eff on the same tensors
+    p = 3
+    h = A.effective_hamiltonian_dmrg(p, para['index1'], para['index2'], para['coeff1'], para['coeff2'], tol=1e-12)
+    host = [be.to_numpy(t) for t in A.mps]
+    O = orc.OracleMps(L, d, para['chi'], [np.real(o) for o in para['op']], mps=host)
+    O.center = A.center
+    h0 = O.dense_effective_hamiltonian(p, para['index1'], para['index2'], para['coeff1'], para['coeff2'], 1e-12)
+    assert np.abs(h - h0).max() < 1e-12 and np.abs(h - h.T).max() < 1e-12
+    x = be.to_numpy(A.mps[p]).reshape(-1)
+    assert abs(x @ h @ x - float(g['e_per_site'][0]) * L) < 1e-9
+
+
+def test_rdm_full_state_dense_heff_and_checks(golden, cpu_be):
+    check_rdm_and_dense_helpers(golden, cpu_be)

@@ -503,7 +503,103 @@ class MpsOpenBoundaryClass(MpsBasic):
             raise RuntimeError('norm_mps needs a centre-orthogonal MPS')
         return self._be.norm(self.mps[self.center])
 
+    def reduced_density_matrix_two_body(self, p1, p2):
+        """rho[(s1 s2), (s1' s2')] of sites p1 < p2, trace 1 (MPSClass.py:841-855).  Computed as the d^4 expectation values
+        of matrix-unit products |s1><s1'| (x) |s2><s2'| in one batched pass of the observable machinery (any centre)."""
+        p1, p2 = int(p1), int(p2)
+        if not 0 <= p1 < p2 < self.length:
+            raise ValueError('reduced_density_matrix_two_body needs 0 <= p1 < p2 < length')
+        self._ensure_device()
+        if self.center < -0.5:
+            raise RuntimeError('observables need a centre-orthogonal MPS; call correct_orthogonal_center first')
+        d = self.phys_dim
+        units = []
+        for a in range(d):
+            for b in range(d):
+                u = np.zeros((d, d))
+                u[a, b] = 1.0
+                units.append(u)
+        terms = [((p1, a * d + ap), (p2, b * d + bp)) for a in range(d) for b in range(d) for ap in range(d) for bp in range(d)]
+        vals = []
+        for i in range(0, len(terms), 1024):
+            vals.append(expect_products(self._be, self.mps, self.center, units, terms[i:i + 1024]))
+        rho = np.concatenate(vals).reshape(d * d, d * d)      # [(a b), (a' b')] = <|a><a'| (x) |b><b'|>
+        return rho / np.trace(rho)
+
+    def full_coefficients_mps(self, tol_memory=20):
+        """the state as a (d^L, 1) column vector, site 0 the slowest index (MPSClass.py:968-987, whose loop forgets to keep
+        its reshape and fails for L > 2; this is what it is meant to return).  None when log2(d^L) - 5 > tol_memory."""
+        if self.length * np.log2(self.phys_dim) - 5 > tol_memory:
+            print('The memory cost of the total coefficients is too large; pass a larger tol_memory to calculate anyway')
+            return None
+        x = np.ones((1, 1))
+        for t in self.mps:
+            t = self._be.to_numpy(t) if hasattr(t, 'data_ptr') else np.asarray(t)
+            x = x.dot(t.reshape(t.shape[0], -1)).reshape(-1, t.shape[2])
+        return x.reshape(-1, 1)
+
+    def effective_hamiltonian_dmrg(self, p, index1, index2, coeff1, coeff2, tol=1e-12):
+        """dense H_eff of site p as an (n, n) numpy array, n = a*d*b (MPSClass.py:532-580; the eig_way = 0 object).  Built by
+        applying the matvec plan to the columns of the identity, so it is the very operator the eigensolver sees; meant
+        for checks at small n (refuses n > 4096)."""
+        self._ensure_device()
+        self.correct_orthogonal_center(p)
+        plan = self.effective_hamiltonian_plan(p, index1, index2, coeff1, coeff2, tol=tol)
+        shape = tuple(self.mps[p].shape)
+        n = int(np.prod(shape))
+        if n > 4096:
+            plan.destroy()
+            raise ValueError('effective_hamiltonian_dmrg: n = %d is too large for a dense matrix (limit 4096)' % n)
+        h = np.zeros((n, n))
+        e = np.zeros(n)
+        for j in range(n):
+            e[:] = 0.0
+            e[j] = 1.0
+            h[:, j] = self._be.to_numpy(plan.matvec(self._be.from_numpy(e.reshape(shape)), 0.0, 1.0)).reshape(-1)
+        plan.destroy()
+        return h
+
+    # ---- checking functions (MPSClass.py:1024-1088) ----
+    def check_orthogonality_by_tensors(self, tol=1e-12, is_print=True):
+        """sites whose isometry property contradicts self.orthogonality (-1: left-, 1: right-orthonormal)"""
+        bad = []
+        for n in range(self.length):
+            t = self._be.to_numpy(self.mps[n]) if hasattr(self.mps[n], 'data_ptr') else np.asarray(self.mps[n])
+            o = int(np.ravel(self.orthogonality)[n])
+            if o == -1:
+                m = t.reshape(-1, t.shape[2])
+                ok = np.abs(m.T @ m - np.eye(m.shape[1])).max() <= tol
+            elif o == 1:
+                m = t.reshape(t.shape[0], -1)
+                ok = np.abs(m @ m.T - np.eye(m.shape[0])).max() <= tol
+            else:
+                ok = True
+            if not ok:
+                bad.append(n)
+        if is_print:
+            print('The orthogonality of all tensors are marked correctly by self.orthogonality' if not bad
+                  else 'In self.orthogonality, the orthogonality of the following tensors is incorrect: ' + str(bad))
+        return bad
+
+    def check_virtual_bond_dimensions(self):
+        bad = [n for n in range(1, self.length)
+               if self.virtual_dim[n] != self.mps[n].shape[0] or self.virtual_dim[n] != self.mps[n - 1].shape[2]]
+        for n in bad:
+            print('BondDimError: inconsistent dimension detected for the %d-th virtual bond' % n)
+        return bad
+
+    def check_mps_norm1(self, if_print=False):
+        norm = self.norm_mps()
+        if abs(norm - 1) > 1e-14:
+            print('The norm is MPS is %g away from 1' % abs(norm - 1))
+        if if_print:
+            print('The norm of MPS is %g' % norm)
+        return norm
+
     # ---- housekeeping ----
+    def print_general_info(self):
+        print('DMRG & MPS (%s): B200-native drop-in of ranshiju/T-Nalg MpsOpenBoundaryClass; see README.md' % self.version)
+
     def report_yourself(self):
         print('center: ' + str(self.center))
         print('orthogonality:' + str(self.orthogonality.T))
