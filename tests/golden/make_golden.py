@@ -235,6 +235,41 @@ def rdm_case():
     return out
 
 
+def tensor_kats():
+    """outputs of the reference's own tensor helpers next to the hot path (a6 + the physical-bond transfers used by the
+    two-body density matrix) on seeded random inputs: TensorBasicModule.py:427-528 (absorb_matrices2tensor[_full_fast]),
+    :622-649 (bound_vec_with_phys_*), :652-674 (transfer_matrix_mps), :755-785 (normalize_tensor), :876-900
+    (check_orthogonality)."""
+    rng = np.random.RandomState(11)
+    out = {}
+    T = rng.randn(4, 3, 5)
+    M = [rng.randn(4, 6), rng.randn(3, 3), rng.randn(5, 2)]
+    out['T'] = T
+    for i, m in enumerate(M):
+        out['M%d' % i] = m
+    out['absorb_all'] = tm.absorb_matrices2tensor(T.copy(), [m.copy() for m in M])
+    out['absorb_full_fast'] = tm.absorb_matrices2tensor_full_fast(T.copy(), [m.copy() for m in M])
+    out['absorb_bonds_2_0'] = tm.absorb_matrices2tensor(T.copy(), [M[2].copy(), M[0].copy()], bonds=[2, 0])
+    v2l, v2r = rng.randn(4, 4), rng.randn(5, 5)
+    v4l, v4r = rng.randn(3, 3, 4, 4), rng.randn(3, 3, 5, 5)
+    out.update(v2l=v2l, v2r=v2r, v4l=v4l, v4r=v4r)
+    out['phys_l2r_empty'] = tm.bound_vec_with_phys_left2right(T)
+    out['phys_l2r_v2'] = tm.bound_vec_with_phys_left2right(T, v2l)
+    out['phys_l2r_v4'] = tm.bound_vec_with_phys_left2right(T, v4l)
+    out['phys_r2l_empty'] = tm.bound_vec_with_phys_right2left(T)
+    out['phys_r2l_v2'] = tm.bound_vec_with_phys_right2left(T, v2r)
+    out['phys_r2l_v4'] = tm.bound_vec_with_phys_right2left(T, v4r)
+    out['transfer_matrix'] = tm.transfer_matrix_mps(T)
+    tn, nrm = tm.normalize_tensor(T.copy())
+    out['normalized'], out['norm'] = tn, nrm
+    q = np.linalg.qr(rng.randn(12, 5))[0].reshape(4, 3, 5)
+    out['Q'] = q
+    out['check_ort_Q_2'] = np.array(bool(tm.check_orthogonality(q, [2], tol=1e-12)))
+    out['check_ort_Q_0'] = np.array(bool(tm.check_orthogonality(q, [0], tol=1e-12)))
+    out['ones_mps_1'] = tm.ones_open_mps(3, 2, 3)[1]
+    return out
+
+
 def main():
     cases = {
         'e2e_chain12': lambda: pack_run(chain_para(l=12, chi=16, **TIGHT), 0),
@@ -246,6 +281,7 @@ def main():
         'docstring_kats': docstring_kats,
         'truncation_lib': truncation_case,
         'rdm_xxz8': rdm_case,
+        'tensor_kats': tensor_kats,
     }
     only = sys.argv[1:]
     for name, fn in cases.items():

@@ -286,3 +286,34 @@ def check_rdm_and_dense_helpers(golden, be):
 
 def test_rdm_full_state_dense_heff_and_checks(golden, cpu_be):
     check_rdm_and_dense_helpers(golden, cpu_be)
+
+
+def check_tensor_helpers(golden, be):
+    """a6 and friends against outputs of the reference's own functions (tests/golden/tensor_kats.npz) and against the
+    integer examples printed in its docstrings (TensorBasicModule.py:476-485,434-441)"""
+    from tnalg_b200 import TensorBasicModule as T
+    g = golden('tensor_kats')
+    M = [g['M0'], g['M1'], g['M2']]
+    assert np.abs(T.absorb_matrices2tensor(g['T'], M) - g['absorb_all']).max() < 1e-12
+    assert np.abs(T.absorb_matrices2tensor_full_fast(g['T'], M) - g['absorb_full_fast']).max() < 1e-12
+    assert np.abs(T.absorb_matrices2tensor(g['T'], [M[2], M[0]], bonds=[2, 0]) - g['absorb_bonds_2_0']).max() < 1e-12
+    ones = np.ones((2, 2, 2))
+    m3 = [np.array([[1., 2], [2, 3]]), np.array([[2., 3], [3, 4]]), np.array([[3., 4], [4, 5]])]
+    assert np.array_equal(np.rint(T.absorb_matrices2tensor_full_fast(ones, m3)), [[[105, 135], [147, 189]], [[175, 225], [245, 315]]])
+    for name, fn, v2, v4 in (('l2r', T.bound_vec_with_phys_left2right, g['v2l'], g['v4l']),
+                             ('r2l', T.bound_vec_with_phys_right2left, g['v2r'], g['v4r'])):
+        assert np.abs(fn(g['T']) - g['phys_%s_empty' % name]).max() < 1e-12
+        assert np.abs(fn(g['T'], v2) - g['phys_%s_v2' % name]).max() < 1e-12
+        assert np.abs(fn(g['T'], v4) - g['phys_%s_v4' % name]).max() < 1e-12
+    out = T.bound_vec_with_phys_left2right(be.from_numpy(g['T']), be.from_numpy(g['v2l']))   # device in -> device out
+    assert hasattr(out, 'data_ptr') and np.abs(be.to_numpy(out) - g['phys_l2r_v2']).max() < 1e-12
+    assert np.abs(T.transfer_matrix_mps(g['T']) - g['transfer_matrix']).max() < 1e-12
+    tn, nrm = T.normalize_tensor(g['T'])
+    assert np.abs(tn - g['normalized']).max() < 1e-15 and abs(nrm - float(g['norm'])) < 1e-13
+    assert T.check_orthogonality(g['Q'], [2], tol=1e-12) == bool(g['check_ort_Q_2'])
+    assert T.check_orthogonality(g['Q'], [0], tol=1e-12) == bool(g['check_ort_Q_0'])
+    assert np.array_equal(T.ones_open_mps(3, 2, 3)[1], g['ones_mps_1'])
+
+
+def test_tensor_helpers_vs_reference_functions(golden, cpu_be):
+    check_tensor_helpers(golden, cpu_be)
