@@ -317,3 +317,25 @@ def check_tensor_helpers(golden, be):
 
 def test_tensor_helpers_vs_reference_functions(golden, cpu_be):
     check_tensor_helpers(golden, cpu_be)
+
+
+def test_small_utilities_keep_reference_behaviour(capsys):
+    """helpers next to the path with the reference's names: values checked against the reference's docstring examples
+    (BasicFunctionsSJR.py:121-133,152-163,204-240,416-437; HamiltonianModule.py:60-72,137-148)"""
+    from tnalg_b200 import BasicFunctionsSJR as B, HamiltonianModule as H, Parameters as Pm
+    assert B.sort_list([1, 2, 'a', 'b'], [1, 3]) == [2, 'b']
+    assert B.remove_element_from_list([1, 2, 3], 3) == [1, 2]
+    assert B.arg_find_list([1, 2, 1, 3], 1, which='last') == [2] and B.arg_find_list([1, 2, 1, 3], 1, n=2) == [0, 2]
+    assert B.print_sep('This is an example', '@', 20) == '@@@@@@@@@@ This is an example @@@@@@@@@@'
+    assert B.print_dict({'name1': 1, 'name2': 'a'}, None, 'this is an example\n', '-') == 'this is an example\nname1-1\nname2-a\n'
+    assert B.print_options(['left', 'right'], [1, 2], 'Where to go:') == 'Where to go:1: left    2: right'
+    assert set(B.info_contact()) == {'name', 'email', 'affiliation'}
+    pairs, n = H.interactions_full_connection_two_body(4)
+    assert n == 6 and pairs.tolist() == [[0, 1], [0, 2], [0, 3], [1, 2], [1, 3], [2, 3]]
+    assert H.from_spin2phys_dim('half') == 2 and H.from_spin2phys_dim('one') == 3
+    h = H.hamiltonian_heisenberg('half', 1, 1, 1, 0, 0)
+    assert np.allclose(np.linalg.eigvalsh(h), [-0.75, 0.25, 0.25, 0.25])          # singlet / triplet of two spins 1/2
+    hz = H.hamiltonian_heisenberg('half', 0, 0, 0, 0, 0.5)
+    assert np.allclose(np.diag(hz), [0.5, 0, 0, -0.5])
+    assert 'The parameters are' in Pm.show_parameters({'l': 4})
+    capsys.readouterr()

@@ -84,3 +84,22 @@ def interactions_position2full_index_heisenberg_two_body(index_pos):
         i, j = int(index_pos[n, 0]), int(index_pos[n, 1])
         rows += [[i, j, 4, 5], [i, j, 5, 4], [i, j, 3, 3]]
     return np.array(rows, dtype=int).reshape(-1, 4)
+
+
+def from_spin2phys_dim(spin):
+    return {'half': 2, 'one': 3}.get(spin)
+
+
+def hamiltonian_heisenberg(spin, jx, jy, jz, hx, hz):
+    """two-site Hamiltonian jx SxSx + jy SySy + jz SzSz + hx (Sx1 + Sx2) + hz (Sz1 + Sz2) (HamiltonianModule.py:67-72)"""
+    op = spin_operators(spin)
+    h = jx * np.kron(op['sx'], op['sx']) + jy * np.kron(op['sy'], op['sy']).real + jz * np.kron(op['sz'], op['sz'])
+    h = h + hx * (np.kron(op['id'], op['sx']) + np.kron(op['sx'], op['id']))
+    h = h + hz * (np.kron(op['id'], op['sz']) + np.kron(op['sz'], op['id']))
+    return h
+
+
+def interactions_full_connection_two_body(l):
+    """([first_site, second_site] for every pair n1 < n2, number of pairs) (HamiltonianModule.py:137-148)"""
+    pairs = np.array([[n1, n2] for n1 in range(l) for n2 in range(n1 + 1, l)], dtype=float).reshape(-1, 2)
+    return pairs, float(pairs.shape[0])

@@ -152,3 +152,8 @@ def check_continuity_pos_h2(pos_h2):
 
 def physical_dim_from_spin(spin):
     return {'half': 2, 'one': 3}.get(spin, False)
+
+
+def show_parameters(para):
+    from .BasicFunctionsSJR import print_dict
+    return print_dict(para, welcome='The parameters are: \n', style_sep=':\n')
