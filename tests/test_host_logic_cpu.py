@@ -339,3 +339,85 @@ def test_small_utilities_keep_reference_behaviour(capsys):
     assert np.allclose(np.diag(hz), [0.5, 0, 0, -0.5])
     assert 'The parameters are' in Pm.show_parameters({'l': 4})
     capsys.readouterr()
+
+
+def _jacobi_rows_numpy(W, tol=5e-15, max_sweeps=60):
+    """numpy emulation of tn_svd_jacobi's round-robin one-sided Jacobi on the ROWS of W (same pair schedule and rotation
+    formula as the unblocked kernel); returns (sweeps, rotated W, accumulated rotations J with W_out = J W_in)"""
+    W = W.copy()
+    n = W.shape[0]
+    J = np.eye(n)
+    for sweep in range(max_sweeps):
+        nrot = 0
+        for rnd in range(n - 1):
+            pq = []
+            for i in range(n // 2):
+                a, b = (rnd % (n - 1), n - 1) if i == 0 else ((rnd + i) % (n - 1), (rnd + n - 1 - i) % (n - 1))
+                pq.append((min(a, b), max(a, b)))
+            P, Q = np.array([p for p, _ in pq]), np.array([q for _, q in pq])
+            X, Y = W[P], W[Q]
+            a, b, g = (X * X).sum(1), (Y * Y).sum(1), (X * Y).sum(1)
+            rot = (a > 0) & (b > 0) & (g * g > tol * tol * a * b)
+            if not rot.any():
+                continue
+            nrot += int(rot.sum())
+            gg = np.where(rot, g, 1.0)
+            zeta = (b - a) / (2 * gg)
+            t = np.where(zeta >= 0, 1.0, -1.0) / (np.abs(zeta) + np.sqrt(1 + zeta ** 2))
+            c = 1 / np.sqrt(1 + t * t)
+            s = c * t
+            c, s = np.where(rot, c, 1.0)[:, None], np.where(rot, s, 0.0)[:, None]
+            W[P], W[Q] = c * X - s * Y, s * X + c * Y
+            JP, JQ = J[P], J[Q]
+            J[P], J[Q] = c * JP - s * JQ, s * JP + c * JQ
+        if nrot == 0:
+            return sweep + 1, W, J
+    return max_sweeps, W, J
+
+
+def test_preconditioned_svd_algebra_and_sweep_counts(golden):
+    """ops.preconditioned_svd (the code the CUDA backend runs, here with numpy callables): exact truncated SVD on random and
+    on real two-site wavefunctions, and the norm-sorted QR steps cut the Jacobi sweeps on the latter"""
+    import torch
+    from tnalg_b200.ops import preconditioned_svd
+    sweeps = []
+
+    def qr(X):
+        q, r = np.linalg.qr(X.numpy())
+        return torch.from_numpy(np.ascontiguousarray(q)), torch.from_numpy(np.ascontiguousarray(r))
+
+    def jacobi(X, k):                      # X (n, n): rows of X^T are rotated, as the kernel does for tall inputs
+        n_sw, W, J = _jacobi_rows_numpy(X.numpy().T.copy())
+        sweeps.append(n_sw)
+        sig = np.linalg.norm(W, axis=1)
+        order = np.argsort(-sig)[:k]
+        U = (W[order] / sig[order, None]).T                      # X = U S Vt with W = J X^T = S U^T
+        return (torch.from_numpy(np.ascontiguousarray(U)), torch.from_numpy(sig[order].copy()),
+                torch.from_numpy(np.ascontiguousarray(J[order])))
+
+    def mm_nn(X, Y):
+        return X @ Y
+
+    def mm_nt(X, Y):
+        return X @ Y.t()
+
+    rng = np.random.RandomState(3)
+    cases = [rng.randn(80, 64), (np.linalg.qr(rng.randn(70, 70))[0] * np.logspace(0, -10, 70)) @ np.linalg.qr(rng.randn(70, 70))[0].T]
+    cases += list(golden('theta_two_site')['theta'])
+    for n_case, A in enumerate(cases):
+        m, n = A.shape
+        for k in (n, n // 2):
+            U, S, Vt = [x.numpy() for x in preconditioned_svd(torch.from_numpy(A.copy()), k, qr, jacobi, mm_nn, mm_nt)]
+            u0, s0, v0 = np.linalg.svd(A, full_matrices=False)
+            assert U.shape == (m, k) and Vt.shape == (k, n)
+            assert np.abs(S - s0[:k]).max() < 1e-13 * s0[0]
+            assert np.abs(U.T @ U - np.eye(k)).max() < 1e-12 and np.abs(Vt @ Vt.T - np.eye(k)).max() < 1e-12
+            assert np.abs((U * S) @ Vt - (u0[:, :k] * s0[:k]) @ v0[:k]).max() < 1e-12 * s0[0]
+    # sweep counts on the real wavefunctions: sorted preconditioning vs the plain double QR
+    for A in golden('theta_two_site')['theta']:
+        sweeps.clear()
+        preconditioned_svd(torch.from_numpy(A.copy()), A.shape[1], qr, jacobi, mm_nn, mm_nt)
+        sorted_sweeps = sweeps[-1]
+        r2 = np.linalg.qr(np.linalg.qr(A)[1].T)[1]
+        plain_sweeps = _jacobi_rows_numpy(r2.copy())[0]           # Jacobi on the columns of R2^T = rows of R2
+        assert sorted_sweeps <= 9 and sorted_sweeps + 3 <= plain_sweeps, (sorted_sweeps, plain_sweeps)

@@ -72,6 +72,31 @@ class EffHPlan:
             pass
 
 
+def preconditioned_svd(A, k, qr, jacobi, mm_nn, mm_nt):
+    """Truncated SVD of a tall A (m >= n) around a one-sided Jacobi kernel, written against callables so that the algebra is
+    unit-tested on the CPU (tests/test_host_logic_cpu.py) with the very code the CUDA backend runs:
+        P1: columns of A sorted by decreasing norm,          A P1 = Q1 R1
+        P2: rows of R1 sorted by decreasing norm,            (P2 R1)^T = Q2 R2
+        Jacobi on the columns of R2^T:                       R2^T = Ux S Vx^T
+        =>  A = (Q1 P2^T Ux) S (P1 Q2 Vx)^T
+    qr(X) -> (Q, R) thin; jacobi(X, k) -> (U (n,k), S (k), Vt (k,n)); mm_nn(X, Y) = X Y; mm_nt(X, Y) = X Y^T.
+    Sorting by norm is the cheap stand-in for a column-pivoted QR: on two-site DMRG wavefunctions (strongly graded, with
+    SU(2) multiplets) it cuts the Jacobi sweeps from 11-13 to 6-8; on synthetic graded matrices it changes nothing."""
+    import torch
+    p1 = torch.argsort((A * A).sum(0), descending=True)
+    Q1, R1 = qr(A.index_select(1, p1).contiguous())              # (m,n), (n,n)
+    p2 = torch.argsort((R1 * R1).sum(1), descending=True)
+    Q2, R2 = qr(R1.index_select(0, p2).t().contiguous())         # (n,n), (n,n)
+    Ux, S, Vtx = jacobi(R2.t().contiguous(), k)                  # (n,k), (k), (k,n)
+    Ux_un = torch.empty_like(Ux)
+    Ux_un[p2] = Ux                                               # P2^T Ux
+    U = mm_nn(Q1.contiguous(), Ux_un)                            # (m,k)
+    Vt_p = mm_nt(Vtx, Q2.contiguous())                           # (k,n) = Vx^T Q2^T
+    Vt = torch.empty_like(Vt_p)
+    Vt[:, p1] = Vt_p                                             # undo the column sort
+    return U, S, Vt
+
+
 class CudaBackend:
     name = 'cuda'
 
@@ -253,11 +278,10 @@ class CudaBackend:
     # ---- a7/a11/a12: factorizations ----
     def svd(self, A, k_keep=None, precondition=True):
         """A (m,n) -> U (m,k), S (k), Vt (k,n) with the k largest singular triplets.
-        One-sided Jacobi (tn_svd_jacobi) after two QR steps (Drmac-Veselic preconditioning):
-            A = Q1 R1,   R1^T = Q2 R2,   Jacobi on the columns of R2^T:  R2^T = Ux S Vx^T   =>   A = (Q1 Ux) S (Q2 Vx)^T.
-        The first triangular factor makes Jacobi converge in ~11 sweeps instead of 20-40 on graded Schmidt spectra, the
-        second one in ~8 (each QR costs about one sweep), and the small Schmidt values keep high relative accuracy.
-        U and Vt are one chain-GEMM call each."""
+        One-sided Jacobi (tn_svd_jacobi) after two QR steps with norm-sorted columns (Drmac-Veselic preconditioning, see
+        preconditioned_svd below): a raw graded matrix needs 20-40 sweeps and loses relative accuracy on the small values, one
+        QR step gives ~11 sweeps, two give ~8; sorting the columns by norm before each QR (a cheap stand-in for column
+        pivoting) brings real two-site wavefunctions from 11-13 sweeps to 6-8.  U and Vt are one chain-GEMM call each."""
         A = A.contiguous()
         m, n = A.shape
         k = min(m, n) if k_keep is None else min(k_keep, m, n)
@@ -265,15 +289,16 @@ class CudaBackend:
             U2, S, Vt2 = self.svd(A.t().contiguous(), k_keep=k, precondition=precondition)
             return Vt2.t().contiguous(), S, U2.t().contiguous()
         if precondition and n > 1:
-            Q1, R1 = self.qr(A)                                  # (m,n), (n,n)
             if n >= 64:
-                Q2, R2 = self.qr(R1.t().contiguous())            # (n,n), (n,n)
-                Ux, S, Vtx = self._jacobi(R2.t().contiguous(), k)   # (n,k), (k), (k,n)
-                U = self.empty(m, k)
-                self._gemm(0, m, k, n, Q1.contiguous(), Ux, n, k, U)            # U = Q1 Ux            (NN)
-                Vt = self.empty(k, n)
-                self._gemm(1, k, n, n, Vtx, Q2.contiguous(), n, n, Vt)          # Vt[j,i] = sum_l Vtx[j,l] Q2[i,l]   (NT)
-                return U, S, Vt
+                def mm_nn(X, Y):   # X (p,q) . Y (q,r)
+                    out = self.empty(X.shape[0], Y.shape[1])
+                    return self._gemm(0, X.shape[0], Y.shape[1], X.shape[1], X.contiguous(), Y.contiguous(), X.shape[1], Y.shape[1], out)
+
+                def mm_nt(X, Y):   # X (p,q) . Y (r,q)^T
+                    out = self.empty(X.shape[0], Y.shape[0])
+                    return self._gemm(1, X.shape[0], Y.shape[0], X.shape[1], X.contiguous(), Y.contiguous(), X.shape[1], Y.shape[1], out)
+                return preconditioned_svd(A, k, self.qr, self._jacobi, mm_nn, mm_nt)
+            Q1, R1 = self.qr(A)                                  # (m,n), (n,n)
             Ux, S, Vtx = self._jacobi(R1.t().contiguous())       # R1^T = Ux S Vtx  =>  A = (Q1 Vtx^T) S Ux^T
             U = self.empty(m, n)
             self._gemm(1, m, n, n, Q1.contiguous(), Vtx, n, n, U)   # U[i,j] = sum_l Q1[i,l] Vtx[j,l]   (NT)
