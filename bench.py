@@ -220,7 +220,8 @@ def run_reference_arm(args, para, workload):
     line = {'impl': 'reference', 'metric': 'dmrg_sweep_matvecs_per_s', 'value': value, 'unit': 'matvec/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': float(np.mean(times)) * 1e3, 'higher_is_better': True,
             'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': workload, 'L': para['l'], 'chi': para['chi'], 'terms': int(para['index2'].shape[0]),
+            'config': {'workload': workload, 'L': para['l'], 'chi': para['chi'], 'd': int(para['d']), 'terms': int(para['index2'].shape[0]),
+                       'eigs_tol': para['eigs_tol'], 'ncv': 20, 'step': 'one full sweep = %d local updates' % (2 * para['l'] - 2),
                        'extrapolated': True},
             'cpu_baseline': {'value': value, 'unit': 'matvec/s', 'cores': threads, 'kind': 'port', 'sample': sample,
                              'gflops_widest': s['flop_rate'] / 1e9},
