@@ -421,3 +421,53 @@ def test_preconditioned_svd_algebra_and_sweep_counts(golden):
         r2 = np.linalg.qr(np.linalg.qr(A)[1].T)[1]
         plain_sweeps = _jacobi_rows_numpy(r2.copy())[0]           # Jacobi on the columns of R2^T = rows of R2
         assert sorted_sweeps <= 9 and sorted_sweeps + 3 <= plain_sweeps, (sorted_sweeps, plain_sweeps)
+
+
+def test_cuda_backend_svd_wrapper_with_stand_in_primitives():
+    """the body of ops.CudaBackend.svd (shape handling, transposed input, truncation, the GEMM wrappers and their leading
+    dimensions) executed on the CPU with stand-ins for the four primitives it calls (`empty`, `_gemm`, `qr`, `_jacobi`)"""
+    import torch
+    from tnalg_b200 import ops
+
+    class Fake:
+        last_svd_sweeps = 0
+
+        def empty(self, *shape):
+            return torch.full(shape, float('nan'), dtype=torch.float64)
+
+        def _gemm(self, mode, M, N, K, A, B, lda, ldb, Cout, deterministic=1):
+            assert A.is_contiguous() and B.is_contiguous() and Cout.shape == (M, N)
+            if mode == 0:      # C = A (M x K, pitch lda) . B (K x N, pitch ldb)
+                assert A.shape == (M, K) and B.shape == (K, N) and lda == K and ldb == N
+                Cout.copy_(A @ B)
+            elif mode == 1:    # C = A (M x K) . B (N x K)^T
+                assert A.shape == (M, K) and B.shape == (N, K) and lda == K and ldb == K
+                Cout.copy_(A @ B.t())
+            else:
+                raise AssertionError(mode)
+            return Cout
+
+        def qr(self, A):
+            q, r = torch.linalg.qr(A, mode='reduced')
+            return q.t().contiguous().t(), r.t().contiguous().t()      # column-major like cuSOLVER's outputs
+
+        def _jacobi(self, A, k_keep=None):
+            u, s, vt = torch.linalg.svd(A, full_matrices=False)
+            k = s.numel() if k_keep is None else k_keep
+            return u[:, :k].contiguous(), s[:k].contiguous(), vt[:k].contiguous()
+
+        svd = ops.CudaBackend.svd
+
+    fake = Fake()
+    rng = np.random.RandomState(5)
+    for (m, n) in [(96, 80), (80, 96), (128, 128), (40, 30), (30, 40), (5, 1), (1, 5)]:
+        A = rng.randn(m, n) * np.logspace(0, -6, n)[None, :]
+        for k in (None, max(1, min(m, n) // 2)):
+            for pre in (True, False):
+                U, S, Vt = [x.numpy() for x in fake.svd(torch.from_numpy(A.copy()), k_keep=k, precondition=pre)]
+                kk = min(m, n) if k is None else k
+                u0, s0, v0 = np.linalg.svd(A, full_matrices=False)
+                assert U.shape == (m, kk) and S.shape == (kk,) and Vt.shape == (kk, n)
+                assert not np.isnan(U).any() and not np.isnan(Vt).any()
+                assert np.abs(S - s0[:kk]).max() < 1e-12 * s0[0]
+                assert np.abs((U * S) @ Vt - (u0[:, :kk] * s0[:kk]) @ v0[:kk]).max() < 1e-11 * s0[0]
