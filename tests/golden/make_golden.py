@@ -8,6 +8,10 @@ nothing here is computed by the oracle or by the CUDA path.
 Cases
   e2e_chain12      BASELINE cfg1: Heisenberg open chain N=12 chi=16, tight tolerances, seed 0
   e2e_xxz10        XXZ (jxy=1,jz=0.5) + hx=0.3 chain N=10 chi=12 (one-body terms, '0_s_0' group)
+  e2e_longrange8   power-law Ising + transverse field ('longRange' generator, 84 terms, 28 pairs), N=8 chi=16, seed 5
+  e2e_square3x2    Heisenberg on the 'square' generator 3x2, chi=8 (exact), seed 6
+  e2e_full6        all-to-all Heisenberg ('full' generator) N=6 -- degenerate singlets: ENERGY parity only
+  e2e_jigsaw7      spin-1 'jigsaw' chain N=7 chi=27 -- possibly degenerate multiplet: ENERGY parity only
   e2e_spin1_chain8 spin-1 Heisenberg open chain N=8 chi=12 (d = 3 path, Parameters.py:440-446), seed 3
   e2e_j1j2_4x2     J1-J2 4x2 'arbitrary' lattice chi=16 = exact (crossing '1_0_1' terms; even site count so
                    the ground state is a unique singlet -- 3x3 has a degenerate doublet)
@@ -270,11 +274,23 @@ def tensor_kats():
     return out
 
 
+def lattice_para(lattice, **kw):
+    para = Pm.generate_parameters_dmrg(lattice)
+    para.update(kw)
+    if lattice == 'square':
+        para['op'] = para['op'][:6]        # the generator appends the field operator on every call (SURVEY 8d gotcha ii)
+    return Pm.make_consistent_parameter_dmrg(para)
+
+
 def main():
     cases = {
         'e2e_chain12': lambda: pack_run(chain_para(l=12, chi=16, **TIGHT), 0),
         'e2e_xxz10': lambda: pack_run(chain_para(l=10, chi=12, jxy=1, jz=0.5, hx=0.3, hz=0, **TIGHT), 1),
         'e2e_j1j2_4x2': lambda: pack_run(j1j2_para(4, 2, 16, **TIGHT), 2),
+        'e2e_longrange8': lambda: pack_run(lattice_para('longRange', l=8, chi=16, jxy=0, jz=1, hx=0.5, hz=0, alpha=1.0, **TIGHT), 5),
+        'e2e_square3x2': lambda: pack_run(lattice_para('square', square_width=3, square_height=2, chi=8, **TIGHT), 6),
+        'e2e_full6': lambda: pack_run(lattice_para('full', l=6, chi=8, **TIGHT), 7),
+        'e2e_jigsaw7': lambda: pack_run(lattice_para('jigsaw', l=7, chi=27, **TIGHT), 8),
         'e2e_spin1_chain8': lambda: pack_run(chain_para(l=8, chi=12, spin=sys.intern('one'), **TIGHT), 3),
         'percall_j1j2': percall_case,
         'pr_fixtures': pr_fixtures,

@@ -28,7 +28,10 @@ def para_from_golden(g, **kw):
                 coeff2=g['coeff2'], chi=int(g['chi']), tau=float(g['tau']), eigs_tol=float(g['eigs_tol']),
                 break_tol=float(g['break_tol']), hx=float(g['hx']), hz=float(g['hz']))
     para.update(kw)
-    return Pm.make_consistent_parameter_dmrg(para)
+    para = Pm.make_consistent_parameter_dmrg(para)
+    if 'positions_h2' in g:
+        para['positions_h2'] = np.asarray(g['positions_h2'])   # bond order of the generator that made the golden ('square' differs)
+    return para
 
 
 def test_parameters_match_reference_generators(golden):
@@ -100,7 +103,7 @@ def test_observables_vs_reference(golden, cpu_be):
         assert np.abs(A.observe_bond_energy(g['index2'], g['coeff2']) - g['ob_eb_full']).max() < 1e-12
 
 
-@pytest.mark.parametrize('case', ['e2e_chain12', 'e2e_xxz10', 'e2e_j1j2_4x2', 'e2e_spin1_chain8'])
+@pytest.mark.parametrize('case', ['e2e_chain12', 'e2e_xxz10', 'e2e_j1j2_4x2', 'e2e_spin1_chain8', 'e2e_longrange8', 'e2e_square3x2'])
 def test_end_to_end_vs_reference(golden, cpu_be, case):
     """dmrg_finite_size through the product's host code: converged energies / spectrum rel 1e-10, observables 1e-8"""
     from tnalg_b200.DMRG_anyH import dmrg_finite_size
@@ -471,3 +474,39 @@ def test_cuda_backend_svd_wrapper_with_stand_in_primitives():
                 assert not np.isnan(U).any() and not np.isnan(Vt).any()
                 assert np.abs(S - s0[:kk]).max() < 1e-12 * s0[0]
                 assert np.abs((U * S) @ Vt - (u0[:, :kk] * s0[:kk]) @ v0[:kk]).max() < 1e-11 * s0[0]
+
+
+@pytest.mark.parametrize('case', ['e2e_full6', 'e2e_jigsaw7'])
+def test_energy_parity_on_degenerate_lattices(golden, cpu_be, case):
+    """all-to-all Heisenberg ('full') and the spin-1 'jigsaw' chain have degenerate ground multiplets: the converged energy
+    is a parity target (1e-10), the observables inside the multiplet are not"""
+    from tnalg_b200.DMRG_anyH import dmrg_finite_size
+    g = golden(case)
+    para = para_from_golden(g)
+    np.random.seed(int(g['seed']))
+    ob, A, info, para = dmrg_finite_size(para)
+    assert abs(ob['e_per_site'][0] - g['e_per_site'][0]) <= 1e-10 * abs(g['e_per_site'][0])
+    assert np.array_equal(A.virtual_dim, g['virtual_dim']) and info['not_converged'] == 0
+
+
+def test_lattice_generators_match_reference_tables(golden):
+    """Parameters.generate_parameters_dmrg / make_consistent_parameter_dmrg for every lattice the reference generates
+    (Parameters.py:64-165,188-277): same index and coefficient tables as the unmodified reference"""
+    from tnalg_b200 import Parameters as Pm
+    cases = {'e2e_longrange8': ('longRange', dict(l=8, chi=16, jxy=0, jz=1, hx=0.5, hz=0, alpha=1.0)),
+             'e2e_square3x2': ('square', dict(square_width=3, square_height=2, chi=8)),
+             'e2e_full6': ('full', dict(l=6, chi=8)),
+             'e2e_jigsaw7': ('jigsaw', dict(l=7, chi=27))}
+    for name, (lattice, kw) in cases.items():
+        g = golden(name)
+        para = Pm.generate_parameters_dmrg(lattice)
+        para.update(kw)
+        if lattice == 'square':
+            para['op'] = para['op'][:6]   # like the reference, the generator appends the field operator on every call
+        para = Pm.make_consistent_parameter_dmrg(para)
+        assert para['l'] == int(g['l']) and para['d'] == int(g['d']), name
+        for k in ('index1', 'index2', 'positions_h2'):
+            assert np.array_equal(np.asarray(para[k]), g[k]), (name, k)
+        for k in ('coeff1', 'coeff2'):
+            assert np.allclose(np.asarray(para[k], dtype=float).reshape(-1), g[k].reshape(-1), rtol=0, atol=1e-15), (name, k)
+        assert len(para['op']) == g['op'].shape[0] and all(np.allclose(a, b) for a, b in zip(para['op'], g['op'])), name

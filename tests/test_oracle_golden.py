@@ -13,6 +13,8 @@ def para_from_golden(g, **kw):
                          eigs_tol=float(g['eigs_tol']), break_tol=float(g['break_tol']),
                          hx=float(g['hx']), hz=float(g['hz']), **kw)
     assert para['l'] == int(g['l'])
+    if 'positions_h2' in g:
+        para['positions_h2'] = np.asarray(g['positions_h2'])   # bond order of the generator that made the golden
     return para
 
 
@@ -104,7 +106,7 @@ def test_percall_observables(golden):
     assert abs(A.norm() - float(g['ob_norm'])) < 1e-13
 
 
-@pytest.mark.parametrize('case', ['e2e_chain12', 'e2e_xxz10', 'e2e_j1j2_4x2', 'e2e_spin1_chain8'])
+@pytest.mark.parametrize('case', ['e2e_chain12', 'e2e_xxz10', 'e2e_j1j2_4x2', 'e2e_spin1_chain8', 'e2e_longrange8', 'e2e_square3x2'])
 def test_end_to_end_against_reference(golden, case):
     """converged tight-tolerance runs: e_per_site / spectrum rel 1e-10, observables abs 1e-8
     (BASELINE.json north_star tolerances)."""
