@@ -12,6 +12,7 @@ Cases
   e2e_square3x2    Heisenberg on the 'square' generator 3x2, chi=8 (exact), seed 6
   e2e_full6        all-to-all Heisenberg ('full' generator) N=6 -- degenerate singlets: ENERGY parity only
   e2e_jigsaw7      spin-1 'jigsaw' chain N=7 chi=27 -- possibly degenerate multiplet: ENERGY parity only
+  e2e_periodic8    XXZ + field ring N=8 (bound_cond='periodic': one long bond (0, N-1) on the open MPS), chi=16, seed 9
   e2e_spin1_chain8 spin-1 Heisenberg open chain N=8 chi=12 (d = 3 path, Parameters.py:440-446), seed 3
   e2e_j1j2_4x2     J1-J2 4x2 'arbitrary' lattice chi=16 = exact (crossing '1_0_1' terms; even site count so
                    the ground state is a unique singlet -- 3x3 has a degenerate doublet)
@@ -291,6 +292,7 @@ def main():
         'e2e_square3x2': lambda: pack_run(lattice_para('square', square_width=3, square_height=2, chi=8, **TIGHT), 6),
         'e2e_full6': lambda: pack_run(lattice_para('full', l=6, chi=8, **TIGHT), 7),
         'e2e_jigsaw7': lambda: pack_run(lattice_para('jigsaw', l=7, chi=27, **TIGHT), 8),
+        'e2e_periodic8': lambda: pack_run(chain_para(l=8, chi=16, bound_cond='periodic', jxy=1, jz=0.8, hx=0.2, hz=0, **TIGHT), 9),
         'e2e_spin1_chain8': lambda: pack_run(chain_para(l=8, chi=12, spin=sys.intern('one'), **TIGHT), 3),
         'percall_j1j2': percall_case,
         'pr_fixtures': pr_fixtures,

@@ -103,7 +103,7 @@ def test_observables_vs_reference(golden, cpu_be):
         assert np.abs(A.observe_bond_energy(g['index2'], g['coeff2']) - g['ob_eb_full']).max() < 1e-12
 
 
-@pytest.mark.parametrize('case', ['e2e_chain12', 'e2e_xxz10', 'e2e_j1j2_4x2', 'e2e_spin1_chain8', 'e2e_longrange8', 'e2e_square3x2'])
+@pytest.mark.parametrize('case', ['e2e_chain12', 'e2e_xxz10', 'e2e_j1j2_4x2', 'e2e_spin1_chain8', 'e2e_longrange8', 'e2e_square3x2', 'e2e_periodic8'])
 def test_end_to_end_vs_reference(golden, cpu_be, case):
     """dmrg_finite_size through the product's host code: converged energies / spectrum rel 1e-10, observables 1e-8"""
     from tnalg_b200.DMRG_anyH import dmrg_finite_size

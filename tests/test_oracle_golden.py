@@ -106,7 +106,7 @@ def test_percall_observables(golden):
     assert abs(A.norm() - float(g['ob_norm'])) < 1e-13
 
 
-@pytest.mark.parametrize('case', ['e2e_chain12', 'e2e_xxz10', 'e2e_j1j2_4x2', 'e2e_spin1_chain8', 'e2e_longrange8', 'e2e_square3x2'])
+@pytest.mark.parametrize('case', ['e2e_chain12', 'e2e_xxz10', 'e2e_j1j2_4x2', 'e2e_spin1_chain8', 'e2e_longrange8', 'e2e_square3x2', 'e2e_periodic8'])
 def test_end_to_end_against_reference(golden, case):
     """converged tight-tolerance runs: e_per_site / spectrum rel 1e-10, observables abs 1e-8
     (BASELINE.json north_star tolerances)."""
