@@ -83,3 +83,21 @@ def test_two_site_truncated_sweep_matches_dense_solve_dmrg(cpu_be):
     sv = np.linalg.svd((psi / np.linalg.norm(psi)).reshape(para['d'] ** (mid + 1), -1), compute_uv=False)[:4]
     assert np.abs(np.asarray(A.lm[mid]) - sv).max() < 1e-7
     assert lm_ref[mid].size == 4
+
+
+@pytest.mark.parametrize('lattice,kw', [('chain', dict(l=8, bound_cond='periodic', jxy=1, jz=0.8, hx=0.2, hz=0)),
+                                        ('longRange', dict(l=8, jxy=0, jz=1, hx=0.5, hz=0, alpha=1.0)),
+                                        ('square', dict(square_width=4, square_height=2))])
+def test_two_site_sweep_on_other_lattices_reaches_exact_energy(cpu_be, lattice, kw):
+    """long bonds (ring closure, power-law couplings, 2D snake): crossing / in-window / window-edge terms of the pair grouping"""
+    from tnalg_b200 import DMRG_anyH, Parameters as Pm
+    para = Pm.generate_parameters_dmrg(lattice)
+    para.update(chi=16, sweep_time=8, dt_ob=1, break_tol=1e-13, eigs_tol=1e-14, **kw)
+    if lattice == 'square':
+        para['op'] = para['op'][:6]
+    para = Pm.make_consistent_parameter_dmrg(para)
+    np.random.seed(3)
+    ob, A, info, _ = DMRG_anyH.dmrg_finite_size_two_site(para, chi_init=2)
+    e0 = np.linalg.eigvalsh(orc.dense_hamiltonian(para))[0]
+    assert abs(float(np.ravel(ob['e_per_site'])[0]) * para['l'] - e0) < 1e-10 * abs(e0)
+    assert max(A.virtual_dim) == 16 and info['not_converged'] == 0
