@@ -331,7 +331,7 @@ class OracleMps:
 
         for n in range(index1.shape[0]):
             pos, sn = int(index1[n, 0]), int(index1[n, 1])
-            c = float(coeff1[n])
+            c = float(np.ravel(coeff1)[n])
             if abs(c) > tol and np.linalg.norm(self.operators[sn]) > tol:
                 vl, vm, vr = self.env_one_body(p, sn, pos)
                 if pos < p:
@@ -341,7 +341,7 @@ class OracleMps:
                 else:
                     acc('0_0_1', vr * c)
         for n in range(index2.shape[0]):
-            c = float(coeff2[n])
+            c = float(np.ravel(coeff2)[n])
             if abs(c) <= tol:
                 continue
             pos = [int(index2[n, 0]), int(index2[n, 1])]
@@ -400,11 +400,11 @@ class OracleMps:
         for n in range(index1.shape[0]):
             if abs(coeff1[n]) > tol and np.linalg.norm(self.operators[int(index1[n, 1])]) > tol:
                 vl, vm, vr = self.env_one_body(p, int(index1[n, 1]), int(index1[n, 0]))
-                h += float(coeff1[n]) * np.kron(np.kron(vl, vm), vr)
+                h += float(np.ravel(coeff1)[n]) * np.kron(np.kron(vl, vm), vr)
         for n in range(index2.shape[0]):
             if abs(coeff2[n]) > tol:
                 vl, vm, vr = self.env_two_body(p, index2[n, 2:4], index2[n, :2])
-                h += float(coeff2[n]) * np.kron(np.kron(vl, vm), vr)
+                h += float(np.ravel(coeff2)[n]) * np.kron(np.kron(vl, vm), vr)
         return h
 
     # ---- local update (update_tensor_eigs, MPSClass.py:778-809) ----
@@ -441,7 +441,7 @@ class OracleMps:
         return np.array([[self.observe_one_body(sn, i)] for i in range(self.length)]).real
 
     def observe_bond_energy(self, index2, coeff2):
-        return np.array([[float(coeff2[n]) * self.observe_two_body(index2[n, 2:], index2[n, :2])]
+        return np.array([[float(np.ravel(coeff2)[n]) * self.observe_two_body(index2[n, 2:], index2[n, :2])]
                          for n in range(index2.shape[0])]).real
 
     def observe_correlators_from_middle(self, op1, op2, ob_len=None):
