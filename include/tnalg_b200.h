@@ -26,7 +26,12 @@
 extern "C" {
 #endif
 
-#define TN_MAX_PHYS_DIM 4 /* d = 2 (spin-1/2), d = 3 (spin-1, Parameters.py:440-446), d = 4 (two spin-1/2 sites of the two-site update) */
+/* physical dimension of a site (or of the combined two-site window): d = 2 (spin-1/2), d = 3 (spin-1,
+ * Parameters.py:440-446), d = 4 (two spin-1/2 sites), d = 9 (two spin-1 sites).  Site operators of dimension up to
+ * TN_MAX_LOADPATH_DIM are applied inside the GEMM operand path; larger ones (effective-Hamiltonian plans only) are applied by
+ * one element-wise pass per operator before the GEMM. */
+#define TN_MAX_PHYS_DIM 9
+#define TN_MAX_LOADPATH_DIM 4
 
 typedef enum {
   TN_OK = 0,
@@ -34,7 +39,8 @@ typedef enum {
   TN_ERR_CUDA = -2,      /* CUDA runtime error, text in tn_last_error() */
   TN_ERR_WORKSPACE = -3, /* workspace too small */
   TN_ERR_NOCONV = -4,    /* iteration limit reached (result is still written) */
-  TN_ERR_DEVICE = -5     /* not an sm_100 device */
+  TN_ERR_DEVICE = -5,    /* not an sm_100 device */
+  TN_ERR_NUMERIC = -6    /* numerical failure (NaN/Inf reached an iteration); outputs are NOT written */
 } tn_status;
 
 const char* tn_last_error(void);
@@ -44,6 +50,9 @@ int tn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* number of kernels this library has launched since tn_launch_count_reset() (bench.py "gpu_launches"). */
 long long tn_launch_count(void);
 void tn_launch_count_reset(void);
+/* on != 0: bit-reproducible mode -- no stream-K split, no FP64-atomic combination of partial tiles, no concurrent matvec
+ * stages (every output tile is summed by one CTA in a fixed order).  Returns the previous setting.  Default off. */
+int tn_set_deterministic(int on);
 
 /* --------------------------------------------------------------------------------------------------
  * Chain GEMM: the FP64 tensor-core (DMMA) contraction engine every tensor-network contraction below is built
@@ -67,7 +76,7 @@ enum { TN_NN = 0, TN_NT = 1, TN_TN = 2 };
 typedef struct {
   const double* A; /* [dev] */
   const double* B; /* [dev] */
-  double op[TN_MAX_PHYS_DIM * TN_MAX_PHYS_DIM]; /* row-major d x d, used when has_op != 0 */
+  double op[TN_MAX_LOADPATH_DIM * TN_MAX_LOADPATH_DIM]; /* row-major d x d (d <= TN_MAX_LOADPATH_DIM), used when has_op != 0 */
   int has_op;
   int reserved;
 } tn_link;
@@ -133,6 +142,10 @@ int tn_trace(const double* E /* [dev] (n,n) */, int n, double* result /* [dev] *
  * the crossing intermediates XL_i psi live in the plan workspace.
  * rank/world shard the links round-robin (multi-GPU): the caller all-reduces `out`; the identity
  * and on-site parts are applied on rank 0 only.
+ * tn_effh_plan_create_rows builds the other multi-GPU decomposition: the plan computes rows [row_begin, row_begin +
+ * row_count) of the (a, d*b) output -- every term, balanced for any number of terms -- from the FULL input psi;
+ * tn_effh_matvec then reads psi_in (a,d,b) and writes the (row_count,d,b) slice to psi_out.  No reduction is needed: the
+ * exchange step becomes an all-gather of the slices of the next Krylov vector (tn_lanczos_lm1 with a tn_comm).
  * -------------------------------------------------------------------------------------------------- */
 typedef struct tn_effh_plan tn_effh_plan;
 
@@ -143,6 +156,13 @@ int tn_effh_plan_create(tn_effh_plan** plan, int a, int d, int b, const double* 
                         int n_rs, const double* const* RS, const double* rs_op, int n_x,
                         const double* const* XL, const double* const* XR, const double* x_coeff /* [host] */,
                         int rank, int world, void* workspace /* [dev] */, size_t workspace_bytes, void* stream);
+int tn_effh_plan_create_rows(tn_effh_plan** plan, int a, int d, int b, const double* HL, const double* HR, const double* M,
+                             int n_ls, const double* const* LS, const double* ls_op, int n_rs, const double* const* RS,
+                             const double* rs_op, int n_x, const double* const* XL, const double* const* XR,
+                             const double* x_coeff, int row_begin, int row_count, void* workspace /* [dev] */,
+                             size_t workspace_bytes, void* stream);
+/* returns 1 for a row-sliced plan (and its slice), 0 for a full / term-sharded plan, negative on error */
+int tn_effh_plan_rows(const tn_effh_plan* plan, int* row_begin, int* row_count);
 int tn_effh_matvec(tn_effh_plan* plan, const double* psi_in /* [dev] */, double* psi_out /* [dev] */, double c_id,
                    double c_h, void* stream);
 /* algorithmic flop of one matvec: 2*a*d*b*[a*(K_L+n_x) + b*(K_R+n_x)], and executed flop. */
@@ -158,16 +178,53 @@ int tn_effh_plan_destroy(tn_effh_plan* plan);
  * the projected tridiagonal eigenproblem and the convergence test stay on the device; the host reads one flag
  * per restart cycle.  Converged when  tau*|beta_m u_m| <= tol * |1 - tau*theta|  (ARPACK's criterion applied to
  * the shifted operator).  ncv = Krylov dimension per cycle (ARPACK default 20), max_restarts cycles at most.
- * allreduce (may be NULL) is called once per matvec on the partial H psi when the plan is sharded.
+ * Multi-GPU (one exchange per Lanczos step, stream-ordered, issued by the library):
+ *   - term-sharded plan + comm: ncclAllReduce of the partial H psi (or the caller's `allreduce` callback, comm == NULL);
+ *   - row-sliced plan + comm:   every rank keeps only its slice of each Krylov vector; ncclAllGather of the slices of v_j
+ *     before the matvec, dot products as two <= (ncv+2)-number all-reduces per step; v0 and vec_out are full vectors,
+ *     bit-identical on all ranks.
  * Blocking: returns after the result is available.  lambda/resid/n_matvec are [host] outputs.
+ * TN_ERR_NOCONV: iteration limit, the best Ritz pair IS written.  TN_ERR_NUMERIC: nothing is written.
  * -------------------------------------------------------------------------------------------------- */
 typedef int (*tn_allreduce_fn)(double* buf /* [dev] */, long long count, void* user, void* stream);
+typedef struct tn_comm tn_comm;
 
 size_t tn_lanczos_workspace_bytes(long long n, int ncv);
+size_t tn_lanczos_workspace_bytes_sharded(const tn_effh_plan* plan, const tn_comm* comm, int ncv);
 int tn_lanczos_lm1(tn_effh_plan* plan, double tau, const double* v0 /* [dev] n */, double tol, int ncv,
                    int max_restarts, double* lambda_out, double* vec_out /* [dev] n */, int* n_matvec_out,
-                   double* resid_out, tn_allreduce_fn allreduce, void* allreduce_user, void* workspace /* [dev] */,
-                   size_t workspace_bytes, void* stream);
+                   double* resid_out, tn_allreduce_fn allreduce, void* allreduce_user, tn_comm* comm,
+                   void* workspace /* [dev] */, size_t workspace_bytes, void* stream);
+
+/* The same solver for a caller-supplied operator y = H x on device vectors (the `lin_map` of eigs_fh,
+ * Eigs_Module_sjr.py:18-58; also the full-space Hamiltonian of the exact-diagonalisation cross-check,
+ * library/EDspinClass.py:69-77).  `locked`: n_locked orthonormal vectors (pitch ld_locked) the search is kept orthogonal
+ * to -- eigenpairs beyond the first are computed by deflation. */
+typedef int (*tn_matvec_fn)(const double* x /* [dev] n */, double* y /* [dev] n */, void* user, void* stream);
+int tn_lanczos_generic(tn_matvec_fn matvec, void* user, long long n, double tau, const double* v0 /* [dev] */, double tol,
+                       int ncv, int max_restarts, const double* locked /* [dev] or NULL */, int n_locked,
+                       long long ld_locked, double* lambda_out, double* vec_out /* [dev] */, int* n_matvec_out,
+                       double* resid_out, void* workspace /* [dev] */, size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------------------
+ * Communicator.  NCCL is bound at run time (dlopen libnccl.so.2; a process that already carries one,
+ * e.g. torch's, shares it).  tn_comm_init adopts a caller-owned ncclComm_t; tn_comm_unique_id + tn_comm_init_rank create
+ * one (the 128-byte id travels through the caller's own bootstrap, e.g. a torch.distributed broadcast).
+ * All collectives are in place on [dev] float64 buffers and stream-ordered.
+ * -------------------------------------------------------------------------------------------------- */
+int tn_comm_unique_id(char* id128 /* [host] 128 bytes out */);
+int tn_comm_init_rank(tn_comm** comm, const char* id128 /* [host] */, int rank, int world);
+int tn_comm_init(tn_comm** comm, void* nccl_comm /* ncclComm_t */, int rank, int world);
+int tn_comm_rank(const tn_comm* comm);
+int tn_comm_world(const tn_comm* comm);
+long long tn_comm_collectives(const tn_comm* comm); /* collectives issued so far through this handle */
+int tn_comm_destroy(tn_comm* comm);
+int tn_comm_allreduce_sum(tn_comm* comm, double* buf /* [dev] */, long long count, void* stream);
+int tn_comm_allgather(tn_comm* comm, const double* send /* [dev] count_per_rank */, double* recv /* [dev] world*count_per_rank */,
+                      long long count_per_rank, void* stream);
+/* n broadcasts in ONE grouped launch (the outgoing operators of a sharded environment update) */
+int tn_comm_broadcast_many(tn_comm* comm, double* const* bufs /* [host] of [dev] */, const long long* counts /* [host] */,
+                           const int* roots /* [host] */, int n, void* stream);
 
 /* --------------------------------------------------------------------------------------------------
  * One-sided Jacobi SVD (a7 'svd' branch, a11, a12): A (m,n) row-major = U diag(S) Vt, singular values sorted
@@ -181,6 +238,46 @@ size_t tn_svd_workspace_bytes(int m, int n);
 int tn_svd_jacobi(const double* A /* [dev] */, int m, int n, int k_keep, double* U /* [dev] */, double* S /* [dev] */,
                   double* Vt /* [dev] */, int* sweeps_out, void* workspace /* [dev] */, size_t workspace_bytes,
                   void* stream);
+
+/* Symmetric eigenproblem on the same Jacobi kernels (the north_star's "Jacobi SVD/eigh"): A (n,n) symmetric -> w (n) ascending,
+ * V (n,n) row-major with eigenvector j in column j.  The dense local solve of eig_way = 0 (MPSClass.py:792-794). Blocking. */
+size_t tn_eigh_workspace_bytes(int n);
+int tn_eigh_jacobi(const double* A /* [dev] */, int n, double* w /* [dev] */, double* V /* [dev] */, int* sweeps_out,
+                   void* workspace /* [dev] */, size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------------------
+ * Householder QR of the gauge moves (a7: np.linalg.qr in left2right/right2left_decompose_tensor,
+ * TensorBasicModule.py:342-345,378-380; every step of the sweep DMRG_anyH.py:47-64 moves the centre with it).
+ * A (m,n) = Q (m,k) R (k,n), k = min(m,n); LAPACK's reflector convention, so R matches np.linalg.qr including row signs for
+ * full-rank input; Q^T Q = 1 to rounding for any conditioning.  Blocked (panel 32): the panel is factored by one thread-block
+ * cluster with one distributed-shared-memory reduction per column, trailing updates and the explicit Q run on FP64 tensor
+ * cores.  Deterministic.  trans_in: the input is stored as A^T (n,m); trans_q: Q is written as Q^T (k,m).
+ * tn_qr_l2r / tn_qr_r2l are the two gauge moves on an MPS tensor T (a,d,b):
+ *   l2r: T.reshape(a*d, b) = Q R        -> Q_out (a,d,k), R_out (k,b)
+ *   r2l: T.reshape(a, d*b)^T = Q R      -> Q_out (k,d,b) (= Q^T), R_out (k,a)
+ * -------------------------------------------------------------------------------------------------- */
+size_t tn_qr_workspace_bytes(int m, int n);
+int tn_qr_householder(const double* A /* [dev] */, int m, int n, int trans_in, double* Q /* [dev] */, int trans_q,
+                      double* R /* [dev] */, void* workspace /* [dev] */, size_t workspace_bytes, void* stream);
+int tn_qr_l2r(const double* T /* [dev] (a,d,b) */, int a, int d, int b, double* Q_out, double* R_out, void* workspace,
+              size_t workspace_bytes, void* stream);
+int tn_qr_r2l(const double* T /* [dev] (a,d,b) */, int a, int d, int b, double* Q_out, double* R_out, void* workspace,
+              size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------------------
+ * Exact-diagonalisation cross-checker (library/EDspinClass.py:69-77 project_all_hamilt and
+ * algorithms/ExactDiagonalizationAlgo.py:12-24 exact_ground_state): the full-space operator on a d^L vector (site 0 slowest)
+ *   out = c_id v + c_h sum_n h[h_index[n]] on sites (p1[n], p2[n]),   hs: n_h matrices (d^2 x d^2), index (s_p1, s_p2),
+ * and its ground state through the device-resident Lanczos (dominant eigenpair of 1 - tau*H, like eigsh(..., which='LM')).
+ * -------------------------------------------------------------------------------------------------- */
+size_t tn_ed_workspace_bytes(int L, int d, int n_terms, int n_h, int ncv);
+int tn_ed_apply(double* out /* [dev] */, const double* v /* [dev] */, int L, int d, int n_terms, const int* p1 /* [host] */,
+                const int* p2 /* [host] */, const int* h_index /* [host] */, const double* hs /* [host] */, int n_h, double c_id,
+                double c_h, void* workspace /* [dev] */, size_t workspace_bytes, void* stream);
+int tn_ed_ground_state(int L, int d, int n_terms, const int* p1, const int* p2, const int* h_index, const double* hs, int n_h,
+                       double tau, const double* v0 /* [dev] */, double tol, int ncv, int max_restarts, double* lambda_out,
+                       double* vec_out /* [dev] */, int* n_matvec_out, double* resid_out, void* workspace /* [dev] */,
+                       size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

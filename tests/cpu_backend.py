@@ -2,8 +2,8 @@
 
 Implements the same interface with numpy (via oracle/dmrg_oracle.py primitives) on CPU torch tensors so that the
 host logic of the product (term algebra, environment bookkeeping, sweep driver, observables, pickling) can be
-exercised by `-m "not gpu"` tests in a container without a GPU.  The product never imports this module; the
-injection point is tnalg_b200.ops.set_backend(), called from tests only.
+exercised by `-m "not gpu"` tests in a container without a GPU.  The product never imports this module and has no
+hook for it: tests replace the process-wide backend object with `install()` below.
 
 `lanczos` is a numpy transcription of the algorithm in tnalg_b200/csrc/lanczos.cu (thick restart, CGS2, ARPACK
 criterion on the shifted operator) so that its convergence behaviour is validated against the reference's results.
@@ -13,6 +13,32 @@ import torch
 from scipy.linalg import eigh_tridiagonal
 
 from oracle import dmrg_oracle as orc
+
+
+def install(be):
+    """make `be` the process-wide backend returned by tnalg_b200.ops.backend() (test-side injection; the product has no
+    backend switch)"""
+    from tnalg_b200 import ops
+    ops._backend = be
+
+
+class GlooComm:
+    """stand-in for tnalg_b200.ops.Comm (the in-library NCCL communicator) on torch.distributed/gloo"""
+
+    def __init__(self, dist):
+        self.dist, self.rank, self.world = dist, dist.get_rank(), dist.get_world_size()
+
+    def allreduce(self, t):
+        self.dist.all_reduce(t)
+        return t
+
+    def broadcast(self, t, src=0):
+        self.dist.broadcast(t, src=src)
+        return t
+
+    def broadcast_many(self, tensors, roots):
+        for t, r in zip(tensors, roots):
+            self.dist.broadcast(t, src=r)
 
 
 def shard_groups(g, rank, world):
@@ -97,7 +123,11 @@ class CpuPlan:
     def matvec(self, psi, c_id=0.0, c_h=1.0, out=None):
         x = psi.numpy().reshape(-1)
         y = (c_id * x if self.rank == 0 else 0.0) + c_h * self.apply(x)
-        return torch.from_numpy(y.reshape(psi.shape))
+        res = torch.from_numpy(y.reshape(psi.shape))
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
 
     def destroy(self):
         pass
@@ -124,6 +154,12 @@ class CpuBackend:
 
     def launch_count(self):
         return 0
+
+    def comm(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return GlooComm(dist)
+        return None
 
     def env_update(self, direction, T, outputs):
         self.n_env_updates += 1
@@ -157,14 +193,15 @@ class CpuBackend:
         return torch.from_numpy(np.ascontiguousarray(orc.mode_product(T.numpy(), mat.numpy(), bond)))
 
     def effh_plan(self, shape, HL=None, HR=None, M=None, LS=(), ls_ops=(), RS=(), rs_ops=(), XL=(), XR=(), x_coeff=(),
-                  rank=0, world=1):
+                  rank=0, world=1, rows=None):
+        assert rows is None, 'the stand-in shards by terms only'
         n = lambda t: None if t is None else t.numpy()  # noqa: E731
         g = {'HL': n(HL), 'HR': n(HR), 'M': None if M is None else np.asarray(M), 'LS': [n(t) for t in LS],
              'ls_ops': [np.asarray(o) for o in ls_ops], 'RS': [n(t) for t in RS], 'rs_ops': [np.asarray(o) for o in rs_ops],
              'XL': [n(t) for t in XL], 'XR': [n(t) for t in XR], 'x_coeff': list(x_coeff)}
         return CpuPlan(tuple(shape), g, rank, world)
 
-    def lanczos(self, plan, tau, v0, tol, ncv=20, max_restarts=1000, allreduce=None):
+    def lanczos(self, plan, tau, v0, tol, ncv=20, max_restarts=1000, comm=None, allreduce=None):
         """numpy transcription of tn_lanczos_lm1 (tnalg_b200/csrc/lanczos.cu)."""
         x0 = v0.numpy().reshape(-1)
         n = x0.size
@@ -180,7 +217,9 @@ class CpuBackend:
             for j in range(j0, m):
                 w = np.ascontiguousarray(plan.apply(V[j]))
                 n_mv += 1
-                if allreduce is not None:
+                if comm is not None:
+                    w = comm.allreduce(torch.from_numpy(w)).numpy()
+                elif allreduce is not None:
                     assert allreduce(w.ctypes.data, w.size, None, None) == 0
                 h = V[:j + 1] @ w
                 w = w - V[:j + 1].T @ h
@@ -222,6 +261,37 @@ class CpuBackend:
     def qr(self, A):
         q, r = np.linalg.qr(A.numpy())
         return torch.from_numpy(np.ascontiguousarray(q)), torch.from_numpy(np.ascontiguousarray(r))
+
+    def qr_tensor(self, T, left2right):
+        a, d, b = T.shape
+        if left2right:
+            q, r = self.qr(T.reshape(a * d, b))
+            return q.reshape(a, d, -1).contiguous(), r
+        q, r = self.qr(T.reshape(a, d * b).t().contiguous())
+        return q.t().contiguous().reshape(-1, d, b), r
+
+    def eigh(self, A):
+        w, v = np.linalg.eigh(A.numpy())
+        return torch.from_numpy(w), torch.from_numpy(np.ascontiguousarray(v))
+
+    def lanczos_generic(self, matvec, n, tau, v0, tol, ncv=20, max_restarts=1000, locked=None):
+        """dense stand-in: build the operator column by column, deflate, diagonalise"""
+        H = np.zeros((n, n))
+        for j in range(n):
+            e = torch.zeros(n, dtype=torch.float64)
+            e[j] = 1.0
+            y = torch.zeros(n, dtype=torch.float64)
+            matvec(e, y)
+            H[:, j] = y.numpy()
+        H = 0.5 * (H + H.T)
+        if locked is not None and locked.shape[0]:
+            Lk = locked.numpy()
+            P = np.eye(n) - Lk.T @ Lk
+            H = P @ H @ P
+            H += 1e6 * (np.sign(tau) or 1.0) * Lk.T @ Lk   # push the deflated directions to the other end of the spectrum
+        w, v = np.linalg.eigh(H)
+        best = int(np.argmax(np.abs(1.0 - tau * w)))
+        return 1.0 - tau * w[best], torch.from_numpy(np.ascontiguousarray(v[:, best])), n, 0.0, True
 
     def scale_diag_rows(self, S, Vt):
         return S[:, None] * Vt

@@ -2,9 +2,9 @@
 writes tests/golden/theta_two_site.npz.  Run from the repository root."""
 import numpy as np, sys
 sys.path.insert(0, '.')
-from tests.cpu_backend import CpuBackend
+from tests.cpu_backend import CpuBackend, install as cpu_backend_install
 from tnalg_b200 import ops, DMRG_anyH, Parameters as Pm
-be = CpuBackend(); ops.set_backend(be)
+be = CpuBackend(); cpu_backend_install(be)
 rec = []
 raw = be.svd
 def svd(A, k_keep=None):

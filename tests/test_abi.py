@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def header_symbols():
     text = open(os.path.join(ROOT, 'include', 'tnalg_b200.h')).read()
     text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
-    return sorted(set(re.findall(r'\b(tn_[a-z0-9_]+)\s*\(', text)) - {'tn_allreduce_fn'})
+    return sorted(set(re.findall(r'\b(tn_[a-z0-9_]+)\s*\(', text)) - {'tn_allreduce_fn', 'tn_matvec_fn'})
 
 
 def test_library_exports_every_declared_symbol():
@@ -54,6 +54,14 @@ def test_bad_arguments_are_errors_not_ub():
     st = lib.tn_svd_jacobi(None, 0, 0, 0, None, None, None, None, None, 0, None)
     assert st == -1
     handle = C.c_void_p()
-    st = lib.tn_effh_plan_create(C.byref(handle), 4, 7, 4, None, None, None, 0, None, None, 0, None, None, 0, None, None,
+    st = lib.tn_effh_plan_create(C.byref(handle), 4, 10, 4, None, None, None, 0, None, None, 0, None, None, 0, None, None,
                                  None, 0, 1, None, 0, None)
     assert st == -1 and b'bad shape' in lib.tn_last_error()
+    st = lib.tn_qr_householder(None, 0, 0, 0, None, 0, None, None, 0, None)
+    assert st == -1 and b'tn_qr_householder' in lib.tn_last_error()
+    st = lib.tn_comm_init(None, None, 0, 1)
+    assert st == -1
+    st = lib.tn_ed_apply(None, None, 4, 2, 0, None, None, None, None, 0, 0.0, 1.0, None, 0, None)
+    assert st == -1
+    assert lib.tn_qr_workspace_bytes(64, 32) > 0 and lib.tn_eigh_workspace_bytes(16) > 0 and lib.tn_ed_workspace_bytes(4, 2, 3, 1, 20) > 0
+    assert lib.tn_set_deterministic(1) == 0 and lib.tn_set_deterministic(0) == 1

@@ -17,11 +17,11 @@ def _worker(rank, world, port, case, q):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
-        from tests.cpu_backend import CpuBackend
+        from tests.cpu_backend import CpuBackend, install as cpu_backend_install
         from tests.test_host_logic_cpu import para_from_golden
         from tnalg_b200 import ops
         from tnalg_b200.DMRG_anyH import dmrg_finite_size
-        ops.set_backend(CpuBackend())
+        cpu_backend_install(CpuBackend())
         g = dict(np.load(os.path.join(ROOT, 'tests', 'golden', case + '.npz')))
         para = para_from_golden(g)
         np.random.seed(int(g['seed']))
@@ -37,11 +37,11 @@ def _worker_two_site(rank, world, port, q):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
-        from tests.cpu_backend import CpuBackend
+        from tests.cpu_backend import CpuBackend, install as cpu_backend_install
         from tests.test_two_site_cpu import small_para
         from tnalg_b200 import ops
         from tnalg_b200.DMRG_anyH import dmrg_finite_size_two_site
-        ops.set_backend(CpuBackend())
+        cpu_backend_install(CpuBackend())
         para = small_para('xxz', chi=16, sweep_time=6, dt_ob=1, break_tol=1e-13, eigs_tol=1e-14)
         np.random.seed(1)
         ob, A, info, para = dmrg_finite_size_two_site(para, chi_init=2)
@@ -86,10 +86,10 @@ def _worker_scan(rank, world, port, tmp, q):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
-        from tests.cpu_backend import CpuBackend
+        from tests.cpu_backend import CpuBackend, install as cpu_backend_install
         from tnalg_b200 import ops
         from tnalg_b200.DMRG_anyH import run_parameter_scan
-        ops.set_backend(CpuBackend())
+        cpu_backend_install(CpuBackend())
         q.put((rank, run_parameter_scan(_scan_paras(tmp), save=True, seed=7)))
     finally:
         dist.destroy_process_group()
@@ -99,7 +99,7 @@ def test_parameter_scan_is_distributed_over_ranks_without_term_sharding(tmp_path
     """independent runs (weak scaling, no data-path collective): every rank reports all runs, energies equal ED, each run
     left its .pr file, and the result equals the serial loop"""
     from oracle import dmrg_oracle as orc
-    from tests.cpu_backend import CpuBackend
+    from tests.cpu_backend import CpuBackend, install as cpu_backend_install
     from tnalg_b200 import BasicFunctionsSJR as bf, ops
     from tnalg_b200.DMRG_anyH import run_parameter_scan
     world, port = 2, 33500 + os.getpid() % 2000
@@ -120,11 +120,11 @@ def test_parameter_scan_is_distributed_over_ranks_without_term_sharding(tmp_path
         saved = bf.load_pr(os.path.join(str(tmp_path), para['data_exp'] + '.pr'))
         assert abs(float(np.ravel(saved['ob']['e_per_site'])[0]) - e) == 0 and saved['A'].length == para['l']
     old = ops._backend
-    ops.set_backend(CpuBackend())
+    cpu_backend_install(CpuBackend())
     try:
         serial = run_parameter_scan(paras, save=False, seed=7)
     finally:
-        ops.set_backend(old)
+        cpu_backend_install(old)
     assert [r[:2] for r in serial] == [r[:2] for r in res[0]]
 
 

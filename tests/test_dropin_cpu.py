@@ -14,9 +14,9 @@ import os, pickle, pickletools, sys
 sys.path.insert(0, %(dropin)r)
 sys.path.insert(0, %(root)r)
 import numpy as np
-from tests.cpu_backend import CpuBackend
+from tests.cpu_backend import CpuBackend, install as cpu_backend_install
 from tnalg_b200 import ops
-ops.set_backend(CpuBackend())                     # host-logic test: no GPU in this container
+cpu_backend_install(CpuBackend())                     # host-logic test: no GPU in this container
 import MPSClass, DMRG_anyH, Parameters as Pm, BasicFunctionsSJR as Bf, HamiltonianModule, TensorBasicModule, Eigs_Module_sjr
 assert MPSClass.MpsOpenBoundaryClass.__module__ == 'MPSClass'
 para = Pm.generate_parameters_dmrg('chain')          # reference testDMRG.py:1-8

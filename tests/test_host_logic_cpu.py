@@ -7,7 +7,7 @@ import pickle
 import numpy as np
 import pytest
 
-from tests.cpu_backend import CpuBackend
+from tests.cpu_backend import CpuBackend, install as cpu_backend_install
 
 
 @pytest.fixture()
@@ -15,9 +15,9 @@ def cpu_be():
     from tnalg_b200 import ops
     old = ops._backend
     be = CpuBackend()
-    ops.set_backend(be)
+    cpu_backend_install(be)
     yield be
-    ops.set_backend(old)
+    cpu_backend_install(old)
 
 
 def para_from_golden(g, **kw):

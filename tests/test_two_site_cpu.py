@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import dmrg_oracle as orc
-from tests.cpu_backend import CpuBackend
+from tests.cpu_backend import CpuBackend, install as cpu_backend_install
 
 
 @pytest.fixture()
@@ -12,9 +12,9 @@ def cpu_be():
     from tnalg_b200 import ops
     old = ops._backend
     be = CpuBackend()
-    ops.set_backend(be)
+    cpu_backend_install(be)
     yield be
-    ops.set_backend(old)
+    cpu_backend_install(old)
 
 
 def small_para(kind, **kw):

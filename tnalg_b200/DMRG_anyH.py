@@ -43,6 +43,7 @@ def dmrg_finite_size(para=None, quiet=True):
             is_parallel=para['isParallel'], par_pool=None, is_save_op=para['is_save_op'], eig_way=para['eigWay'],
             is_env_parallel_lmr=para['isParallelEnvLMR'])
     A.shard_terms = bool(para.get('shard_terms', True))   # False: independent runs per rank (parameter scans)
+    A.sync_replicas()     # sharded runs work on bit-identical replicas: rank 0's random start goes to every rank
     A.correct_orthogonal_center(para['ob_position'])
     e0_per_site = 0
     info['convergence'] = 1
@@ -99,6 +100,7 @@ def dmrg_finite_size_two_site(para=None, chi_init=None, quiet=True):
             is_parallel=para['isParallel'], par_pool=None, is_save_op=para['is_save_op'], eig_way=para['eigWay'],
             is_env_parallel_lmr=para['isParallelEnvLMR'])
     A.shard_terms = bool(para.get('shard_terms', True))
+    A.sync_replicas()
     A.correct_orthogonal_center(0)
     info = {'convergence': 1, 'n_sweeps': 0}
     ob, e0 = dict(), 0

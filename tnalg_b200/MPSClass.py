@@ -180,16 +180,21 @@ class MpsOpenBoundaryClass(MpsBasic):
         be = self._be
         T = self.mps[n]
         a, d, b = T.shape
+        if not (self.decomp_way == 1 or self.decomp_way == 'svd'):
+            Qt, R = be.qr_tensor(T, left2right)          # tn_qr_l2r / tn_qr_r2l (Householder, own kernels)
+            return Qt, R, R.shape[0], np.zeros(0)
         mat = T.reshape(a * d, b) if left2right else T.reshape(a, d * b).t().contiguous()
         k = min(mat.shape)
-        if self.decomp_way == 1 or self.decomp_way == 'svd':
-            U, S, Vt = be.svd(mat)
-            R = be.scale_diag_rows(S, Vt)
-            lm = be.to_numpy(S)
-            Q = U
-        else:
-            Q, R = be.qr(mat)
-            lm = np.zeros(0)
+        U, S, Vt = be.svd(mat)
+        R = be.scale_diag_rows(S, Vt)
+        lm = be.to_numpy(S)
+        Q = U
+        if lm.size and lm.min() <= 1e-14 * lm.max() * max(mat.shape):
+            # numerically rank-deficient (e.g. ini_way='1'): the Jacobi kernel returns zero columns of U for zero singular
+            # values, np.linalg.svd an orthonormal completion.  One Householder QR of U completes the basis, U = Q2 R2 with
+            # R2 = diag(+-1) on the kept directions and 0 elsewhere, so T = Q2 (R2 S Vt) is unchanged and Q2 is an isometry.
+            Q, R2 = be.qr(U.contiguous())
+            R = be.mode_product(R.contiguous().reshape(k, 1, -1), R2.t().contiguous(), 0).reshape(k, -1)   # R2 . (S Vt)
         if left2right:
             Qt = Q.contiguous().reshape(a, d, k)
         else:
@@ -279,70 +284,121 @@ class MpsOpenBoundaryClass(MpsBasic):
 
     # ---- a1/a2/a8: the local update (update_tensor_eigs, MPSClass.py:778-809) ----
     def _environments(self, index1, index2, coeff1, coeff2, tol):
-        key = (id(index1), id(index2), id(coeff1), id(coeff2), float(tol), len(self.operators))
+        # keyed on CONTENT (the reference rebuilds its environments from coeff* on every call, MPSClass.py:633-682): an
+        # in-place edit of the coupling arrays or of an operator (parameter ramps that reuse the dict) must not be missed
+        import hashlib
+        h = hashlib.blake2b(digest_size=16)
+        for arr in (index1, index2, coeff1, coeff2):
+            h.update(np.ascontiguousarray(np.asarray(arr, dtype=float)).tobytes())
+            h.update(b'|')
+        for o in self.operators:
+            h.update(np.ascontiguousarray(np.asarray(o, dtype=complex)).tobytes())
+        key = (h.digest(), float(tol))
         if self._env is None or self._env_key != key:
             terms = TermTable(index1, index2, coeff1, coeff2, self.operators, tol)
             if terms.length > self.length:
                 raise ValueError('coupling terms reference site %d but the MPS has %d sites' % (terms.length - 1, self.length))
             self._env = EnvCache(self._be, terms, self.length)
-            self._env.dist = self._dist()
+            self._env.comm = self._comm()
             self._env_key = key
-            self._env_refs = (index1, index2, coeff1, coeff2)  # keep the ids alive
         return self._env
 
-    def _dist(self):
-        try:
-            import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and getattr(self, 'shard_terms', True):
-                return dist
-        except Exception:
-            pass
-        return None
+    def _comm(self):
+        """the backend's communicator when the local problems of this MPS are sharded over the ranks (multi-GPU)"""
+        if not getattr(self, 'shard_terms', True):
+            return None
+        return self._be.comm()
 
-    def effective_hamiltonian_plan(self, p, index1, index2, coeff1, coeff2, tol=1e-12, rank=0, world=1):
+    def sync_replicas(self, src=0):
+        """make every rank hold rank `src`'s tensors (one grouped broadcast).  The sharded path assumes bit-identical
+        replicas; dmrg_finite_size calls this after drawing the random initial state, so ranks need not share a seed."""
+        comm = self._comm()
+        if comm is not None:
+            self._ensure_device()
+            comm.broadcast_many(list(self.mps), [src] * self.length)
+            if self._env is not None:
+                self._env.invalidate_all()
+
+    def effective_hamiltonian_plan(self, p, index1, index2, coeff1, coeff2, tol=1e-12, rank=0, world=1, rows=None):
         """tn_effh_plan for site p (the opt_env groups of all_environments_optimized, MPSClass.py:633-682)."""
         self._ensure_device()
         env = self._environments(index1, index2, coeff1, coeff2, tol)
-        return env.plan(p, self.mps, rank=rank, world=world)
+        return env.plan(p, self.mps, rank=rank, world=world, rows=rows)
+
+    def _solve(self, make_plan, shape, v0, tau, tol):
+        """dominant eigenvector of 1 - tau*H_eff for the local problem whose plan `make_plan(rank, world, rows)` builds.
+        Multi-GPU: row-sliced plans + sliced Krylov basis ('rows'), or term-sharded plans + all-reduce ('terms'); sites too
+        small to slice are solved by every rank and re-synchronised from rank 0.  All collectives are issued by the library."""
+        import torch
+        be = self._be
+        comm = self._comm()
+        a, d, b = shape
+        rows, plan_comm, resync = None, None, False
+        if comm is None:
+            plan = make_plan(0, 1, None)
+        else:
+            mode = getattr(be, 'shard_mode', 'terms')
+            rows = be.shard_rows(a, d, b, comm.rank, comm.world) if mode == 'rows' else None
+            if rows is not None:
+                plan, plan_comm = make_plan(0, 1, rows), comm
+            elif mode == 'terms':
+                plan, plan_comm = make_plan(comm.rank, comm.world, None), comm
+            else:
+                plan, resync = make_plan(0, 1, None), True
+        n = a * d * b
+        if self.timing:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        if self.eig_way == 0 and comm is None:
+            lam, vec, n_mv, resid, ok = self._dense_solve(plan, shape, v0, tau)
+        else:
+            lam, vec, n_mv, resid, ok = be.lanczos(plan, tau, v0.reshape(-1), tol, ncv=self.lanczos_ncv,
+                                                   max_restarts=self.lanczos_max_restarts, comm=plan_comm)
+        if self.timing:
+            e1.record()
+            self._events.append((e0, e1))
+        if resync or (plan_comm is not None and rows is None):
+            comm.broadcast(vec, src=0)   # replicated or all-reduced solves: keep the replicas bit-identical
+        self.stats['n_solves'] += 1
+        self.stats['n_matvec'] += n_mv
+        self.stats['flops_algorithmic'] += n_mv * plan.flops_algorithmic   # whole job (all ranks together)
+        self.stats['flops_executed'] += n_mv * plan.flops_executed         # this rank
+        self.stats['not_converged'] += 0 if ok else 1
+        self.last_eig = {'lambda': lam, 'residual': resid, 'n_matvec': n_mv, 'converged': ok, 'n': n,
+                         'sharding': 'none' if comm is None else ('rows' if rows is not None else ('terms' if plan_comm else 'replicated'))}
+        plan.destroy()
+        return vec
+
+    def _dense_solve(self, plan, shape, v0, tau):
+        """eig_way = 0 (MPSClass.py:792-794): the explicit matrix 1 - tau*H_eff and its dominant eigenvector, here by the
+        Jacobi eigensolver (tn_eigh_jacobi).  Small local problems only, as in the reference (O(n^2) memory)."""
+        import torch
+        be = self._be
+        n = int(np.prod(shape))
+        if n > 4096:
+            raise ValueError('eig_way=0 builds the dense (n, n) effective Hamiltonian; n = %d is too large (limit 4096), use eig_way=1' % n)
+        eye = torch.eye(n, dtype=torch.float64, device=be.device)
+        h = be.empty(n, n)
+        for j in range(n):
+            plan.matvec(eye[j].reshape(shape), 1.0, -float(tau), out=h[j].reshape(shape))   # row j = column j (symmetric)
+        h = 0.5 * (h + h.t())
+        w, V = be.eigh(h.contiguous())
+        w_host = be.to_numpy(w)
+        best = int(np.argmax(np.abs(w_host)))
+        vec = V[:, best].contiguous()
+        if float((vec * v0.reshape(-1)).sum()) < 0:
+            vec = -vec
+        return float(w_host[best]), vec, n, 0.0, True
 
     def update_tensor_eigs(self, p, index1, index2, coeff1, coeff2, tau, is_real, tol=1e-16):
-        import torch
         self._ensure_device()
         if self.center < -0.5:
             raise RuntimeError('CenterError: central-orthogonalize MPS before updating the tensor')
         self.correct_orthogonal_center(p)
-        dist = self._dist()
-        rank, world = (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
-        plan = self.effective_hamiltonian_plan(p, index1, index2, coeff1, coeff2, tol=tol, rank=rank, world=world)
+        env = self._environments(index1, index2, coeff1, coeff2, tol)
         shape = tuple(self.mps[p].shape)
-        allreduce = None
-        if dist is not None:
-            dev = self._be.device
-
-            def allreduce(buf, count, user, stream):
-                try:
-                    t = _alias_tensor(buf, count, dev)
-                    dist.all_reduce(t)
-                    return 0
-                except Exception:  # pragma: no cover
-                    return 1
-        if self.timing:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        lam, vec, n_mv, resid, ok = self._be.lanczos(plan, tau, self.mps[p].reshape(-1), tol, ncv=self.lanczos_ncv,
-                                                     max_restarts=self.lanczos_max_restarts, allreduce=allreduce)
-        if self.timing:
-            e1.record()
-            self._events.append((e0, e1))
-        if dist is not None:
-            dist.broadcast(vec, src=0)  # keep the replicas bit-identical
-        self.stats['n_solves'] += 1
-        self.stats['n_matvec'] += n_mv
-        self.stats['flops_algorithmic'] += n_mv * plan.flops_algorithmic
-        self.stats['flops_executed'] += n_mv * plan.flops_executed
-        self.stats['not_converged'] += 0 if ok else 1
-        self.last_eig = {'lambda': lam, 'residual': resid, 'n_matvec': n_mv, 'converged': ok}
-        plan.destroy()
+        vec = self._solve(lambda rank, world, rows: env.plan(p, self.mps, rank=rank, world=world, rows=rows), shape,
+                          self.mps[p], tau, tol)
         self.mps[p] = vec.reshape(shape)
         if self.eig_way == 1:
             self.opt_env = dict()
@@ -352,54 +408,25 @@ class MpsOpenBoundaryClass(MpsBasic):
     def update_two_sites_eigs(self, p, index1, index2, coeff1, coeff2, tau, is_real, tol=1e-16, chi=None, to_right=True):
         """optimise theta = mps[p] . mps[p+1] as the dominant eigenvector of 1 - tau*H_eff(two sites) and split it back with
         an SVD truncated to chi.  The centre ends on p+1 (to_right) or p."""
-        import torch
         self._ensure_device()
         be = self._be
         if self.center < -0.5:
             raise RuntimeError('CenterError: central-orthogonalize MPS before updating the tensor')
         if not 0 <= p < self.length - 1:
             raise ValueError('two-site update needs 0 <= p < length-1')
-        from ._lib import MAX_D
-        if self.phys_dim ** 2 > MAX_D and type(be).__name__ == 'CudaBackend':
-            raise NotImplementedError('two-site update: combined physical dimension d*d = %d exceeds TN_MAX_PHYS_DIM = %d '
-                                      '(spin-1/2 only; use the one-site sweep for spin-1)' % (self.phys_dim ** 2, MAX_D))
+        from ._lib import MAX_PHYS_D
+        if self.phys_dim ** 2 > MAX_PHYS_D:
+            raise ValueError('two-site update: combined physical dimension d*d = %d exceeds TN_MAX_PHYS_DIM = %d'
+                             % (self.phys_dim ** 2, MAX_PHYS_D))
         self.correct_orthogonal_center(p)
         env = self._environments(index1, index2, coeff1, coeff2, tol)
-        dist = self._dist()
-        rank, world = (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
         a, d, k = self.mps[p].shape
         b = self.mps[p + 1].shape[2]
         chi = self.virtual_dim.max() if chi is None else chi
-        plan = env.plan_two_site(p, self.mps, rank=rank, world=world)
         # theta[(a s1), (s2 b)] = sum_k T_p[(a s1), k] T_{p+1}[k, (s2 b)]
         theta = be.mode_product(self.mps[p].reshape(a * d, 1, k), self.mps[p + 1].reshape(k, d * b), 2)
-        allreduce = None
-        if dist is not None:
-            dev = be.device
-
-            def allreduce(buf, count, user, stream):
-                try:
-                    dist.all_reduce(_alias_tensor(buf, count, dev))
-                    return 0
-                except Exception:  # pragma: no cover
-                    return 1
-        if self.timing:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        lam, vec, n_mv, resid, ok = be.lanczos(plan, tau, theta.reshape(-1), tol, ncv=self.lanczos_ncv,
-                                               max_restarts=self.lanczos_max_restarts, allreduce=allreduce)
-        if self.timing:
-            e1.record()
-            self._events.append((e0, e1))
-        if dist is not None:
-            dist.broadcast(vec, src=0)
-        self.stats['n_solves'] += 1
-        self.stats['n_matvec'] += n_mv
-        self.stats['flops_algorithmic'] += n_mv * plan.flops_algorithmic
-        self.stats['flops_executed'] += n_mv * plan.flops_executed
-        self.stats['not_converged'] += 0 if ok else 1
-        self.last_eig = {'lambda': lam, 'residual': resid, 'n_matvec': n_mv, 'converged': ok}
-        plan.destroy()
+        vec = self._solve(lambda rank, world, rows: env.plan_two_site(p, self.mps, rank=rank, world=world, rows=rows),
+                          (a, d * d, b), theta, tau, tol)
         kk = int(min(chi, a * d, d * b))
         U, S, Vt = be.svd(vec.reshape(a * d, d * b), k_keep=kk)          # Jacobi SVD, truncated to chi
         s_norm = be.norm(S)
@@ -458,6 +485,11 @@ class MpsOpenBoundaryClass(MpsBasic):
             raise RuntimeError('observables need a centre-orthogonal MPS; call correct_orthogonal_center first')
         ops = [np.real(np.asarray(o)).astype(float) if np.abs(np.imag(np.asarray(o))).max() == 0 else None
                for o in self.operators]
+        for term in terms:
+            for _, sn in term:
+                if ops[int(sn)] is None:
+                    raise ValueError('operator %d is complex (e.g. sy); the real (is_real) path of this implementation cannot '
+                                     'measure it -- see DESIGN.md, out of scope' % int(sn))
         out = []
         for i in range(0, len(terms), 1024):
             out.append(expect_products(self._be, self.mps, self.center, ops, terms[i:i + 1024]))
@@ -616,18 +648,3 @@ class MpsOpenBoundaryClass(MpsBasic):
         self.pool = None
         self._env = None
         self._env_key = None
-
-
-def _alias_tensor(ptr, count, device):
-    """torch view of `count` float64 values at device address `ptr` (used by the all-reduce callback)."""
-    import torch
-    if torch.device(device).type == 'cpu':  # host logic tests (gloo): alias ordinary memory
-        import ctypes
-        buf = (ctypes.c_double * int(count)).from_address(int(ptr))
-        return torch.from_numpy(np.ctypeslib.as_array(buf))
-
-    class _Holder:
-        pass
-    h = _Holder()
-    h.__cuda_array_interface__ = {'shape': (int(count),), 'typestr': '<f8', 'data': (int(ptr), False), 'version': 2}
-    return torch.as_tensor(h, device=device)

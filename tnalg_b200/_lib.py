@@ -8,7 +8,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('TNALG_B200_LIB', os.path.join(HERE, 'libtnalg_b200.so'))  # override: kernel-variant experiments
 
-MAX_D = 4
+MAX_D = 4          # TN_MAX_LOADPATH_DIM: site operators applied inside the GEMM operand path (tn_link.op)
+MAX_PHYS_D = 9     # TN_MAX_PHYS_DIM: effective-Hamiltonian plans and the element-wise site-operator kernel
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)
@@ -26,6 +27,8 @@ class TnProblem(C.Structure):
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p)
+MATVEC_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
+c_longlong_p = C.POINTER(C.c_longlong)
 
 # name -> (restype, argtypes); must list every symbol of include/tnalg_b200.h (tests/test_abi.py checks that)
 SIGNATURES = {
@@ -34,6 +37,7 @@ SIGNATURES = {
     'tn_device_info': (C.c_int, [c_int_p, c_int_p, c_int_p]),
     'tn_launch_count': (C.c_longlong, []),
     'tn_launch_count_reset': (None, []),
+    'tn_set_deterministic': (C.c_int, [C.c_int]),
     'tn_chain_gemm_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),
     'tn_chain_gemm': (C.c_int, [C.c_int] * 8 + [C.POINTER(TnProblem), C.c_int, C.POINTER(TnLink), C.c_int, C.c_int,
                                               C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -50,14 +54,46 @@ SIGNATURES = {
                                       C.c_int, c_void_pp, c_double_p, C.c_int, c_void_pp, c_double_p,
                                       C.c_int, c_void_pp, c_void_pp, c_double_p, C.c_int, C.c_int,
                                       C.c_void_p, C.c_size_t, C.c_void_p]),
+    'tn_effh_plan_create_rows': (C.c_int, [c_void_pp, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, c_double_p,
+                                           C.c_int, c_void_pp, c_double_p, C.c_int, c_void_pp, c_double_p,
+                                           C.c_int, c_void_pp, c_void_pp, c_double_p, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_size_t, C.c_void_p]),
+    'tn_effh_plan_rows': (C.c_int, [C.c_void_p, c_int_p, c_int_p]),
     'tn_effh_matvec': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]),
     'tn_effh_plan_flops': (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
     'tn_effh_plan_uses_tma': (C.c_int, [C.c_void_p]),
     'tn_effh_plan_destroy': (C.c_int, [C.c_void_p]),
     'tn_lanczos_workspace_bytes': (C.c_size_t, [C.c_longlong, C.c_int]),
+    'tn_lanczos_workspace_bytes_sharded': (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_int]),
     'tn_lanczos_lm1': (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_double, C.c_int, C.c_int, c_double_p,
-                                 C.c_void_p, c_int_p, c_double_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                 C.c_void_p, c_int_p, c_double_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                  C.c_void_p]),
+    'tn_lanczos_generic': (C.c_int, [MATVEC_FN, C.c_void_p, C.c_longlong, C.c_double, C.c_void_p, C.c_double, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_int, C.c_longlong, c_double_p, C.c_void_p, c_int_p, c_double_p, C.c_void_p,
+                                     C.c_size_t, C.c_void_p]),
+    'tn_comm_unique_id': (C.c_int, [C.c_char_p]),
+    'tn_comm_init_rank': (C.c_int, [c_void_pp, C.c_char_p, C.c_int, C.c_int]),
+    'tn_comm_init': (C.c_int, [c_void_pp, C.c_void_p, C.c_int, C.c_int]),
+    'tn_comm_rank': (C.c_int, [C.c_void_p]),
+    'tn_comm_world': (C.c_int, [C.c_void_p]),
+    'tn_comm_collectives': (C.c_longlong, [C.c_void_p]),
+    'tn_comm_destroy': (C.c_int, [C.c_void_p]),
+    'tn_comm_allreduce_sum': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    'tn_comm_allgather': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    'tn_comm_broadcast_many': (C.c_int, [C.c_void_p, c_void_pp, c_longlong_p, c_int_p, C.c_int, C.c_void_p]),
+    'tn_eigh_workspace_bytes': (C.c_size_t, [C.c_int]),
+    'tn_eigh_jacobi': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, c_int_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'tn_qr_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),
+    'tn_qr_householder': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
+                                    C.c_void_p]),
+    'tn_qr_l2r': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'tn_qr_r2l': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'tn_ed_workspace_bytes': (C.c_size_t, [C.c_int] * 5),
+    'tn_ed_apply': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p, c_double_p, C.c_int,
+                              C.c_double, C.c_double, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'tn_ed_ground_state': (C.c_int, [C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p, c_double_p, C.c_int, C.c_double, C.c_void_p,
+                                     C.c_double, C.c_int, C.c_int, c_double_p, C.c_void_p, c_int_p, c_double_p, C.c_void_p, C.c_size_t,
+                                     C.c_void_p]),
     'tn_svd_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),
     'tn_svd_jacobi': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, c_int_p,
                                 C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -14,7 +14,8 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libtnalg_b200.so')
 STAMP = os.path.join(HERE, 'csrc', '.build_stamp')
-SOURCES = ['lib.cu', 'chain_gemm.cu', 'chain_gemm_tma.cu', 'vector_ops.cu', 'effh_plan.cu', 'lanczos.cu', 'jacobi_svd.cu']
+SOURCES = ['lib.cu', 'chain_gemm.cu', 'chain_gemm_tma.cu', 'vector_ops.cu', 'effh_plan.cu', 'lanczos.cu', 'jacobi_svd.cu', 'comm.cu',
+           'qr_householder.cu', 'ed_apply.cu', 'jacobi_eigh.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-cudart', 'shared',
               '-Xcompiler', '-fPIC', '-I', os.path.join(ROOT, 'include'), '-I', CSRC]
 
@@ -40,6 +41,8 @@ def build(force=False, verbose=True):
     objs = []
     procs = []
     for src in SOURCES:
+        if not os.path.isfile(os.path.join(CSRC, src)):
+            raise RuntimeError('missing CUDA source %s' % src)
         obj = os.path.join(CSRC, src.replace('.cu', '.o'))
         objs.append(obj)
         cmd = [nvcc] + NVCC_FLAGS + ['-c', os.path.join(CSRC, src), '-o', obj]
@@ -56,7 +59,7 @@ def build(force=False, verbose=True):
             print('nvcc failed for %s:\n%s' % (src, out), file=sys.stderr)
     if failed:
         raise RuntimeError('nvcc compilation failed')
-    cmd = [nvcc, '-shared', '-cudart', 'shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB] + objs
+    cmd = [nvcc, '-shared', '-cudart', 'shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB] + objs + ['-ldl']
     if verbose:
         print(' '.join(cmd), flush=True)
     subprocess.check_call(cmd)

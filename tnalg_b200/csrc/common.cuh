@@ -15,6 +15,9 @@ namespace tn {
 void set_error(const char* fmt, ...);
 extern std::atomic<long long> g_launches;
 int sm_count();
+// tn_set_deterministic(1): no stream-K split, no FP64-atomic combination of partial tiles, no concurrent stages -- every
+// result is bit-reproducible from run to run (costs L2 operand sharing in the right matvec stage)
+bool deterministic_mode();
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
@@ -87,7 +90,8 @@ constexpr int kBK = TN_BK;
 constexpr int kTileBM = TN_CFGL_BM, kTileBN = TN_CFGL_BN, kTileCtas = TN_CFGL_CTAS;
 
 // ---- device-side descriptors of the chain GEMM (built by the host wrappers in chain_gemm.cu) ----
-constexpr int kMaxD = TN_MAX_PHYS_DIM;
+constexpr int kMaxD = TN_MAX_LOADPATH_DIM;  // operators applied inside the GEMM operand path
+constexpr int kMaxPhys = TN_MAX_PHYS_DIM;   // element-wise site-operator kernels, effective-Hamiltonian plans
 constexpr int kOpSlot = 24;   // doubles per operator slot in shared memory: kMaxD^2 entries + the has_op flag at [kOpFlag]
 constexpr int kOpFlag = 16;
 static_assert(kMaxD * kMaxD <= kOpFlag && kOpFlag < kOpSlot, "operator slot layout");

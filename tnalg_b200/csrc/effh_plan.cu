@@ -24,6 +24,17 @@ struct tn_effh_plan {
   int a, d, b;
   long long n;
   int rank, world;
+  // row-sliced plan (multi-GPU 'rows' sharding): this plan computes rows [row_begin, row_begin + a_out) of the (a, d*b)
+  // output from the FULL input psi; a_out == a and row_begin == 0 otherwise
+  bool rows;
+  int row_begin, a_out;
+  long long off, n_out;  // element offset of the slice inside psi, slice length
+  // d > TN_MAX_LOADPATH_DIM (two-site window of spin-1, d = 9): the site operators are applied by one element-wise pass per
+  // operator into pre_buf before the GEMMs, which then run without an operator (launch d = 1)
+  bool preop;
+  int n_pre_l, n_pre_r;
+  std::vector<SiteOp> pre_ops;
+  double* pre_buf;
   SiteOp M;
   bool has_M;
   bool haveA, haveB;
@@ -62,7 +73,8 @@ extern "C" size_t tn_effh_plan_workspace_bytes(int a, int d, int b, int n_ls, in
   size_t n = (size_t)a * d * b;
   return align_up(sizeof(ProblemDev) * (size_t)(1 + n_x)) + align_up(sizeof(LinkDev) * (size_t)(1 + n_ls + n_x)) +
          align_up(sizeof(ProblemDev) * (size_t)(1 + n_rs + n_x)) + align_up(sizeof(LinkDev) * (size_t)(1 + n_rs + n_x)) +
-         align_up(sizeof(double) * n * (size_t)std::max(n_x, 0)) + align_up(sizeof(TmaMap) * (size_t)(3 * (2 + n_ls + n_rs + 2 * n_x))) + 1024;
+         align_up(sizeof(double) * n * (size_t)std::max(n_x, 0)) + align_up(sizeof(TmaMap) * (size_t)(3 * (2 + n_ls + n_rs + 2 * n_x))) +
+         (d > kMaxD ? align_up(sizeof(double) * n * (size_t)(n_ls + n_rs) + 8) : 0) + 1024;
 }
 
 static void set_link(LinkDev& L, const double* A, const double* B, int a_dyn, int b_dyn, const double* op, int d) {
@@ -76,14 +88,20 @@ static void set_link(LinkDev& L, const double* A, const double* B, int a_dyn, in
     for (int i = 0; i < d * d; ++i) L.op[i] = op[i];
 }
 
-extern "C" int tn_effh_plan_create(tn_effh_plan** out_plan, int a, int d, int b, const double* HL, const double* HR,
-                                   const double* M, int n_ls, const double* const* LS, const double* ls_op, int n_rs,
-                                   const double* const* RS, const double* rs_op, int n_x, const double* const* XL,
-                                   const double* const* XR, const double* x_coeff, int rank, int world, void* workspace,
-                                   size_t workspace_bytes, void* stream_) {
+static int plan_create_impl(tn_effh_plan** out_plan, int a, int d, int b, const double* HL, const double* HR,
+                            const double* M, int n_ls, const double* const* LS, const double* ls_op, int n_rs,
+                            const double* const* RS, const double* rs_op, int n_x, const double* const* XL,
+                            const double* const* XR, const double* x_coeff, int rank, int world, int row_begin, int row_count,
+                            void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool rows = row_count >= 0;
+  if (rows) TN_REQUIRE(row_begin >= 0 && row_count > 0 && row_begin + row_count <= a, "tn_effh_plan_create_rows: bad row slice [%d, %d) of %d", row_begin, row_begin + row_count, a);
+  const int a_out = rows ? row_count : a;
+  const long long roff = rows ? (long long)row_begin * a : 0;  // element offset of the row slice inside an (a, a) left block
   TN_REQUIRE(out_plan, "tn_effh_plan_create: null plan pointer");
-  TN_REQUIRE(a > 0 && b > 0 && d >= 1 && d <= kMaxD, "tn_effh_plan_create: bad shape (%d,%d,%d)", a, d, b);
+  TN_REQUIRE(a > 0 && b > 0 && d >= 1 && d <= kMaxPhys, "tn_effh_plan_create: bad shape (%d,%d,%d)", a, d, b);
+  const bool preop = d > kMaxD;
+  const int dl = preop ? 1 : d;  // physical dimension the GEMM launches see
   TN_REQUIRE(n_ls >= 0 && n_rs >= 0 && n_x >= 0, "tn_effh_plan_create: negative counts");
   TN_REQUIRE(n_ls == 0 || (LS && ls_op), "tn_effh_plan_create: LS/ls_op missing");
   TN_REQUIRE(n_rs == 0 || (RS && rs_op), "tn_effh_plan_create: RS/rs_op missing");
@@ -97,6 +115,8 @@ extern "C" int tn_effh_plan_create(tn_effh_plan** out_plan, int a, int d, int b,
   tn_effh_plan* P = new tn_effh_plan();
   P->a = a; P->d = d; P->b = b; P->n = (long long)a * d * b;
   P->rank = rank; P->world = world;
+  P->rows = rows; P->row_begin = rows ? row_begin : 0; P->a_out = a_out;
+  P->off = rows ? (long long)row_begin * d * b : 0; P->n_out = (long long)a_out * d * b;
   P->has_M = M != nullptr;
   std::memset(&P->M, 0, sizeof(P->M));
   if (M) for (int i = 0; i < d * d; ++i) P->M.m[i] = M[i];
@@ -106,10 +126,20 @@ extern "C" int tn_effh_plan_create(tn_effh_plan** out_plan, int a, int d, int b,
   P->linkA = cw.take<LinkDev>(1 + n_ls + n_x);
   P->probB = cw.take<ProblemDev>(1 + n_rs + n_x);
   P->linkB = cw.take<LinkDev>(1 + n_rs + n_x);
-  P->phi = cw.take<double>((size_t)P->n * std::max(n_x, 0) + 1);
+  P->phi = cw.take<double>((size_t)P->n_out * std::max(n_x, 0) + 1);
   P->maps = cw.take<TmaMap>((size_t)(3 * (2 + n_ls + n_rs + 2 * n_x)));
   P->tmaA = P->tmaB = false;
-  if (!P->probA || !P->linkA || !P->probB || !P->linkB || !P->phi || !P->maps) {
+  P->preop = preop; P->n_pre_l = preop ? n_ls : 0; P->n_pre_r = preop ? n_rs : 0;
+  P->pre_buf = preop ? cw.take<double>((size_t)P->n * (size_t)(n_ls + n_rs) + 1) : nullptr;
+  if (preop) {
+    P->pre_ops.resize((size_t)(n_ls + n_rs));
+    for (int k = 0; k < n_ls + n_rs; ++k) {
+      const double* src = k < n_ls ? ls_op + (size_t)k * d * d : rs_op + (size_t)(k - n_ls) * d * d;
+      std::memset(&P->pre_ops[k], 0, sizeof(SiteOp));
+      for (int i = 0; i < d * d; ++i) P->pre_ops[k].m[i] = src[i];
+    }
+  }
+  if (!P->probA || !P->linkA || !P->probB || !P->linkB || !P->phi || !P->maps || (preop && !P->pre_buf)) {
     delete P;
     set_error("tn_effh_plan_create: workspace carve failed");
     return TN_ERR_WORKSPACE;
@@ -121,11 +151,16 @@ extern "C" int tn_effh_plan_create(tn_effh_plan** out_plan, int a, int d, int b,
   // ---- left stage: chain into `out`, then one problem per owned crossing term ----
   int idx = 0;
   int chain_links = 0;
-  if (HL && owns(idx, rank, world)) { set_link(L, HL, nullptr, 0, 1, nullptr, d); la.push_back(L); ++chain_links; }
+  if (HL && owns(idx, rank, world)) { set_link(L, HL + roff, nullptr, 0, 1, nullptr, d); la.push_back(L); ++chain_links; }
   ++idx;
   for (int k = 0; k < n_ls; ++k, ++idx) {
     TN_REQUIRE(LS[k], "tn_effh_plan_create: LS[%d] is null", k);
-    if (owns(idx, rank, world)) { set_link(L, LS[k], nullptr, 0, 1, ls_op + (size_t)k * d * d, d); la.push_back(L); ++chain_links; }
+    if (owns(idx, rank, world)) {
+      if (preop) set_link(L, LS[k] + roff, P->pre_buf + (size_t)k * P->n, 0, 0, nullptr, d);  // LS_k . (op_k psi), op_k psi precomputed
+      else set_link(L, LS[k] + roff, nullptr, 0, 1, ls_op + (size_t)k * d * d, d);
+      la.push_back(L);
+      ++chain_links;
+    }
   }
   if (chain_links) {
     ProblemDev q{};
@@ -137,14 +172,18 @@ extern "C" int tn_effh_plan_create(tn_effh_plan** out_plan, int a, int d, int b,
   ++idx;
   for (int k = 0; k < n_rs; ++k, ++idx) {
     TN_REQUIRE(RS[k], "tn_effh_plan_create: RS[%d] is null", k);
-    if (owns(idx, rank, world)) { set_link(L, nullptr, RS[k], 1, 0, rs_op + (size_t)k * d * d, d); lb.push_back(L); }
+    if (owns(idx, rank, world)) {
+      if (preop) set_link(L, P->pre_buf + (size_t)(n_ls + k) * P->n + P->off, RS[k], 0, 0, nullptr, d);
+      else set_link(L, nullptr, RS[k], 1, 0, rs_op + (size_t)k * d * d, d);
+      lb.push_back(L);
+    }
   }
   int n_phi = 0;
   for (int i = 0; i < n_x; ++i, ++idx) {
     TN_REQUIRE(XL[i] && XR[i], "tn_effh_plan_create: crossing term %d has a null matrix", i);
     if (!owns(idx, rank, world)) continue;
-    double* phi_i = P->phi + (size_t)n_phi * P->n;
-    set_link(L, XL[i], nullptr, 0, 1, nullptr, d);
+    double* phi_i = P->phi + (size_t)n_phi * P->n_out;
+    set_link(L, XL[i] + roff, nullptr, 0, 1, nullptr, d);
     ProblemDev q{};
     q.C = phi_i; q.alpha = x_coeff[i]; q.link_begin = (int)la.size(); q.link_count = 1; q.accumulate = 0; q.c_dyn = 0;
     la.push_back(L);
@@ -158,14 +197,15 @@ extern "C" int tn_effh_plan_create(tn_effh_plan** out_plan, int a, int d, int b,
   P->haveB = !lb.empty();
   // independent stages (no crossing term feeds the right stage) of a small site: both add into `out` with atomics and run
   // on two streams (chi = 256 chain: 2 x 22 us of latency-bound launches per matvec overlap)
-  P->overlapAB = P->haveA && P->haveB && n_phi == 0 && (long long)a * d * b <= (1LL << 19) && !getenv("TNALG_NO_OVERLAP");
+  P->overlapAB = P->haveA && P->haveB && n_phi == 0 && P->n_out <= (1LL << 19) && !deterministic_mode() && !getenv("TNALG_NO_OVERLAP");
   if (P->overlapAB)
     for (auto& q : pa) q.shared_out = 1;
   const double* fake_psi = reinterpret_cast<const double*>(uintptr_t(256));  // alignment stand-in for scheduling
+  const double* fake_slice = fake_psi + (P->off & 1);                         // the right stage reads psi + off
   const bool use_tma = tma_available() && !getenv("TNALG_NO_TMA");
   std::vector<TmaMap> hmaps;
   if (P->haveA) {
-    P->LA = GemmLaunch{TN_NN, a, d * b, a, d, a, d * b, d * b, (int)pa.size(), (int)la.size(), 0};
+    P->LA = GemmLaunch{TN_NN, a_out, d * b, a, dl, a, d * b, d * b, (int)pa.size(), (int)la.size(), deterministic_mode() ? 1 : 0};
     int st = gemm_plan_schedule(P->LA, pa.data(), la.data(), fake_psi, fake_psi, &P->SA);
     if (st != TN_OK) { delete P; return st; }
     if (use_tma && P->SA.config == 0 && P->SA.aligned16) {  // left stage: A = environment matrix (a x a), B = psi (per call)
@@ -173,7 +213,12 @@ extern "C" int tn_effh_plan_create(tn_effh_plan** out_plan, int a, int d, int b,
       for (auto& l : la) {
         l.a_map = (int)hmaps.size();
         hmaps.emplace_back();
-        if (tma_encode_2d(&hmaps.back(), l.A, a, a, a, tma_box_rows_a()) != TN_OK) { P->tmaA = false; break; }
+        if (tma_encode_2d(&hmaps.back(), l.A, a_out, a, a, tma_box_rows_a()) != TN_OK) { P->tmaA = false; break; }
+        if (!l.b_dyn) {  // pre-applied operator: the B operand is a fixed buffer of the plan
+          l.b_map = (int)hmaps.size();
+          hmaps.emplace_back();
+          if (tma_encode_3d(&hmaps.back(), l.B, a, dl, (long long)(d / dl) * b, (long long)d * b) != TN_OK) { P->tmaA = false; break; }
+        }
       }
     }
     TN_CUDA(cudaMemcpyAsync(P->probA, pa.data(), sizeof(ProblemDev) * pa.size(), cudaMemcpyHostToDevice, stream));
@@ -188,10 +233,12 @@ extern "C" int tn_effh_plan_create(tn_effh_plan** out_plan, int a, int d, int b,
     // then keeps all CTAs inside one chunk; a stream-K split would spread them over all chunks again.
     const int nl = (int)lb.size();
     int kChunk = 3;
-    {
+    if (deterministic_mode()) {
+      kChunk = nl;  // one problem, one CTA per output tile, fixed summation order (no FP64 atomics)
+    } else {
       const int BMt = kTileBM, BNt = kTileBN;  // tile of the large configuration
-      const int BMe = d > 1 ? (BMt / d) * d : BMt;
-      const long long tiles = (long long)((a * d + BMe - 1) / BMe) * ((b + BNt - 1) / BNt);
+      const int BMe = dl > 1 ? (BMt / dl) * dl : BMt;
+      const long long tiles = (long long)((a_out * d + BMe - 1) / BMe) * ((b + BNt - 1) / BNt);
       const long long G = (long long)kTileCtas * sm_count();
       double best = -1.0;
       for (int ch = 4; ch >= 1; --ch) {
@@ -207,8 +254,8 @@ extern "C" int tn_effh_plan_create(tn_effh_plan** out_plan, int a, int d, int b,
       q.shared_out = (nl > kChunk || P->overlapAB) ? 1 : 0;
       pb.push_back(q);
     }
-    P->LB = GemmLaunch{TN_NT, a * d, b, b, d, b, b, b, (int)pb.size(), nl, 0};
-    int st = gemm_plan_schedule(P->LB, pb.data(), lb.data(), fake_psi, fake_psi, &P->SB);
+    P->LB = GemmLaunch{TN_NT, a_out * d, b, b, dl, b, b, b, (int)pb.size(), nl, deterministic_mode() ? 1 : 0};
+    int st = gemm_plan_schedule(P->LB, pb.data(), lb.data(), fake_slice, fake_psi, &P->SB);
     if (st != TN_OK) { delete P; return st; }
     if (use_tma && P->SB.config == 0 && P->SB.aligned16) {  // right stage: A = psi (per call) or Phi_i, B = environment matrix (b x b)
       P->tmaB = true;
@@ -216,7 +263,7 @@ extern "C" int tn_effh_plan_create(tn_effh_plan** out_plan, int a, int d, int b,
         if (!l.a_dyn) {
           l.a_map = (int)hmaps.size();
           hmaps.emplace_back();
-          if (tma_encode_2d(&hmaps.back(), l.A, (long long)a * d, b, b, tma_box_rows_a()) != TN_OK) { P->tmaB = false; break; }
+          if (tma_encode_2d(&hmaps.back(), l.A, (long long)a_out * d, b, b, tma_box_rows_a()) != TN_OK) { P->tmaB = false; break; }
         }
         l.b_map = (int)hmaps.size();
         hmaps.emplace_back();
@@ -230,9 +277,35 @@ extern "C" int tn_effh_plan_create(tn_effh_plan** out_plan, int a, int d, int b,
     TN_CUDA(cudaMemcpyAsync(P->maps, hmaps.data(), sizeof(TmaMap) * hmaps.size(), cudaMemcpyHostToDevice, stream));
   const double KL = (HL ? 1 : 0) + n_ls, KR = (HR ? 1 : 0) + n_rs;
   P->alg_flops = 2.0 * a * d * b * ((double)a * (KL + n_x) + (double)b * (KR + n_x));
-  P->exec_flops = 2.0 * a * d * b * ((double)a * (double)la.size() + (double)b * (double)lb.size());
+  P->exec_flops = 2.0 * a_out * d * b * ((double)a * (double)la.size() + (double)b * (double)lb.size());
   *out_plan = P;
   return TN_OK;
+}
+
+extern "C" int tn_effh_plan_create(tn_effh_plan** out_plan, int a, int d, int b, const double* HL, const double* HR,
+                                   const double* M, int n_ls, const double* const* LS, const double* ls_op, int n_rs,
+                                   const double* const* RS, const double* rs_op, int n_x, const double* const* XL,
+                                   const double* const* XR, const double* x_coeff, int rank, int world, void* workspace,
+                                   size_t workspace_bytes, void* stream_) {
+  return plan_create_impl(out_plan, a, d, b, HL, HR, M, n_ls, LS, ls_op, n_rs, RS, rs_op, n_x, XL, XR, x_coeff, rank, world, 0, -1,
+                          workspace, workspace_bytes, stream_);
+}
+
+extern "C" int tn_effh_plan_create_rows(tn_effh_plan** out_plan, int a, int d, int b, const double* HL, const double* HR,
+                                        const double* M, int n_ls, const double* const* LS, const double* ls_op, int n_rs,
+                                        const double* const* RS, const double* rs_op, int n_x, const double* const* XL,
+                                        const double* const* XR, const double* x_coeff, int row_begin, int row_count,
+                                        void* workspace, size_t workspace_bytes, void* stream_) {
+  TN_REQUIRE(row_count > 0, "tn_effh_plan_create_rows: empty row slice");
+  return plan_create_impl(out_plan, a, d, b, HL, HR, M, n_ls, LS, ls_op, n_rs, RS, rs_op, n_x, XL, XR, x_coeff, 0, 1, row_begin,
+                          row_count, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int tn_effh_plan_rows(const tn_effh_plan* P, int* row_begin, int* row_count) {
+  TN_REQUIRE(P, "tn_effh_plan_rows: null plan");
+  if (row_begin) *row_begin = P->row_begin;
+  if (row_count) *row_count = P->a_out;
+  return P->rows ? 1 : 0;
 }
 
 extern "C" int tn_effh_matvec(tn_effh_plan* P, const double* psi_in, double* psi_out, double c_id, double c_h, void* stream_) {
@@ -243,11 +316,21 @@ extern "C" int tn_effh_matvec(tn_effh_plan* P, const double* psi_in, double* psi
     TN_REQUIRE(((reinterpret_cast<uintptr_t>(psi_in) | reinterpret_cast<uintptr_t>(psi_out)) & 15) == 0,
                "tn_effh_matvec: psi_in/psi_out must be 16-byte aligned for this plan");
   // identity + on-site part (rank 0 only when sharded); doubles as the zero-initialisation of `out`
+  // a row-sliced plan reads the full psi_in and writes rows [row_begin, row_begin + a_out) into psi_out (the slice buffer)
   const bool lead = P->rank == 0;
-  TN_CHECK(launch_site_op_axpby(psi_out, psi_in, P->a, P->d, P->b, lead ? c_id : 0.0, (lead && P->has_M) ? c_h : 0.0, P->M, stream));
+  const double* psi_slice = psi_in + P->off;
+  TN_CHECK(launch_site_op_axpby(psi_out, psi_slice, P->a_out, P->d, P->b, lead ? c_id : 0.0, (lead && P->has_M) ? c_h : 0.0, P->M, stream));
   TmaMap psi_a, psi_b;  // psi as the A operand of the right stage / the (k, s, y) B operand of the left stage
-  if (P->tmaA) TN_CHECK(tma_encode_3d(&psi_b, psi_in, P->a, P->d, P->b, (long long)P->d * P->b));
-  if (P->tmaB) TN_CHECK(tma_encode_2d(&psi_a, psi_in, (long long)P->a * P->d, P->b, P->b, tma_box_rows_a()));
+  const int dl = P->preop ? 1 : P->d;
+  if (P->tmaA) TN_CHECK(tma_encode_3d(&psi_b, psi_in, P->a, dl, (long long)(P->d / dl) * P->b, (long long)P->d * P->b));
+  if (P->preop) {  // op_k psi for the '1_s_0' links (all rows: B operand of the left stage) and the '0_s_1' links (this slice)
+    for (int k = 0; k < P->n_pre_l; ++k)
+      TN_CHECK(launch_site_op_axpby(P->pre_buf + (size_t)k * P->n, psi_in, P->a, P->d, P->b, 0.0, 1.0, P->pre_ops[k], stream));
+    for (int k = 0; k < P->n_pre_r; ++k)
+      TN_CHECK(launch_site_op_axpby(P->pre_buf + (size_t)(P->n_pre_l + k) * P->n + P->off, psi_slice, P->a_out, P->d, P->b, 0.0, 1.0,
+                                    P->pre_ops[P->n_pre_l + k], stream));
+  }
+  if (P->tmaB) TN_CHECK(tma_encode_2d(&psi_a, psi_slice, (long long)P->a_out * P->d, P->b, P->b, tma_box_rows_a()));
   SideStream* side = P->overlapAB ? side_stream() : nullptr;
   cudaStream_t streamB = stream;
   if (side) {  // fork: the right stage runs on the side stream after the init kernel
@@ -257,13 +340,13 @@ extern "C" int tn_effh_matvec(tn_effh_plan* P, const double* psi_in, double* psi
   }
   if (side && P->haveB) {
     if (P->tmaB)
-      TN_CHECK(gemm_launch_tma(P->LB, P->SB, P->probB, P->linkB, P->maps, psi_a, psi_b, psi_in, psi_out, c_h, streamB));
+      TN_CHECK(gemm_launch_tma(P->LB, P->SB, P->probB, P->linkB, P->maps, psi_a, psi_b, psi_slice, psi_out, c_h, streamB));
     else
-      TN_CHECK(gemm_launch(P->LB, P->SB, P->probB, P->linkB, psi_in, psi_out, c_h, streamB));
+      TN_CHECK(gemm_launch(P->LB, P->SB, P->probB, P->linkB, psi_slice, psi_out, c_h, streamB));
     TN_CUDA(cudaEventRecord(side->join, streamB));
   }
   if (P->haveA) {
-    if (P->SA.split && P->n_phi > 0) TN_CUDA(cudaMemsetAsync(P->phi, 0, sizeof(double) * (size_t)P->n * P->n_phi, stream));
+    if (P->SA.split && P->n_phi > 0) TN_CUDA(cudaMemsetAsync(P->phi, 0, sizeof(double) * (size_t)P->n_out * P->n_phi, stream));
     if (P->tmaA)
       TN_CHECK(gemm_launch_tma(P->LA, P->SA, P->probA, P->linkA, P->maps, psi_a, psi_b, psi_in, psi_out, c_h, stream));
     else
@@ -273,9 +356,9 @@ extern "C" int tn_effh_matvec(tn_effh_plan* P, const double* psi_in, double* psi
     TN_CUDA(cudaStreamWaitEvent(stream, side->join, 0));  // join
   } else if (P->haveB) {
     if (P->tmaB)
-      TN_CHECK(gemm_launch_tma(P->LB, P->SB, P->probB, P->linkB, P->maps, psi_a, psi_b, psi_in, psi_out, c_h, stream));
+      TN_CHECK(gemm_launch_tma(P->LB, P->SB, P->probB, P->linkB, P->maps, psi_a, psi_b, psi_slice, psi_out, c_h, stream));
     else
-      TN_CHECK(gemm_launch(P->LB, P->SB, P->probB, P->linkB, psi_in, psi_out, c_h, stream));
+      TN_CHECK(gemm_launch(P->LB, P->SB, P->probB, P->linkB, psi_slice, psi_out, c_h, stream));
   }
   return TN_OK;
 }
@@ -297,6 +380,10 @@ extern "C" int tn_effh_plan_destroy(tn_effh_plan* P) {
 // internal accessors for the Lanczos driver
 namespace tn {
 long long plan_dim(const tn_effh_plan* P) { return P->n; }
+bool plan_is_rows(const tn_effh_plan* P) { return P->rows; }
+long long plan_slice_offset(const tn_effh_plan* P) { return P->off; }
+long long plan_slice_len(const tn_effh_plan* P) { return P->n_out; }
+int plan_world(const tn_effh_plan* P) { return P->world; }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -13,6 +13,7 @@
 
 #include <cooperative_groups.h>
 
+#include "comm.cuh"
 #include "common.cuh"
 #include "host_math.h"
 #include "vector_ops.cuh"
@@ -21,12 +22,16 @@ namespace cg = cooperative_groups;
 
 namespace tn {
 long long plan_dim(const tn_effh_plan* P);
+bool plan_is_rows(const tn_effh_plan* P);
+long long plan_slice_offset(const tn_effh_plan* P);
+long long plan_slice_len(const tn_effh_plan* P);
 
 struct LanczosState {
   double alpha[kMaxNcv];
   double beta[kMaxNcv];   // beta[j] couples v_j and v_{j+1}
   double h[kMaxNcv + 2];  // CGS pass 1 coefficients; h[j+1] = w.w of step j (DGKS test)
-  double h2[kMaxNcv + 1]; // CGS pass 2 coefficients
+  double h2[kMaxNcv + 2]; // CGS pass 2 coefficients; sharded path: h2[j+1] = w'.w' after the first pass
+  double lock_h[kMaxNcv]; // coefficients against locked (deflated) vectors, tn_lanczos_generic
   double u[kMaxNcv];      // Ritz vector in the Krylov basis
   double nrm2, inv_beta;
   int need2, pad2;        // DGKS: second Gram-Schmidt pass needed for the current step
@@ -73,6 +78,37 @@ __global__ void lanczos_finish_step_kernel(LanczosState* st, int j) {
       st->beta[j] = 0.0;
     }
     st->inv_beta = 0.0;  // v_{j+1} = 0: later steps of this cycle are inert
+  } else {
+    st->inv_beta = 1.0 / bj;
+  }
+}
+
+// Row-sharded basis (every rank holds a slice of each Krylov vector): step j after BOTH Gram-Schmidt passes were applied.
+// h2[j+1] holds the all-reduced w'.w' measured after the first pass, so |w''|^2 = w'.w' - sum h2_i^2 (Pythagoras) costs no
+// third collective.  It is accurate when the second pass removed little; if it removed more than half of |w'|^2 the vector
+// is numerically inside span(V) and the step is a breakdown (the DGKS rule ARPACK applies after its second pass).
+__global__ void lanczos_finish_sharded_kernel(LanczosState* st, int j) {
+  const double a = st->h[j] + st->h2[j];
+  st->alpha[j] = a;
+  const double w1 = st->h2[j + 1];
+  double s = 0.0;
+  for (int i = 0; i <= j; ++i) s += st->h2[i] * st->h2[i];
+  double n2 = w1 - s;
+  const bool inside = !(n2 > 0.5 * w1);
+  if (n2 < 0.0) n2 = 0.0;
+  st->nrm2 = n2;
+  const double bj = sqrt(n2);
+  st->beta[j] = bj;
+  double scale = fabs(a);
+  if (j > 0) scale = fmax(scale, fabs(st->beta[j - 1]));
+  scale = fmax(scale, 1e-300);
+  if (st->breakdown || inside || bj <= 1e-14 * scale) {
+    if (!st->breakdown) {
+      st->breakdown = 1;
+      st->m_eff = j + 1;
+      st->beta[j] = 0.0;
+    }
+    st->inv_beta = 0.0;
   } else {
     st->inv_beta = 1.0 / bj;
   }
@@ -268,55 +304,99 @@ struct LanczosStatus {
   int converged, breakdown, m_eff, ql_fail;
 };
 
-}  // namespace tn
+// What the driver needs from an operator: y_loc = H x, where x is Krylov vector `x_loc` (this rank's slice, or the whole
+// vector when nothing is sharded) and y_loc the matching slice of the result.
+struct LanczosOp {
+  tn_effh_plan* plan = nullptr;      // effective-Hamiltonian plan (full, term-sharded or row-sliced)
+  tn_matvec_fn fn = nullptr;         // or a caller-supplied operator (tn_lanczos_generic)
+  void* fn_user = nullptr;
+  tn_allreduce_fn allreduce = nullptr;  // term-sharded plan, caller's collective
+  void* allreduce_user = nullptr;
+  tn_comm* comm = nullptr;           // in-library collectives
+  bool rows = false;                 // row-sliced plan: gather the slices of x into `full`, apply the plan to it
+  double* full = nullptr;            // world * n_pad doubles
+  long long n = 0, n_pad = 0;
 
-using namespace tn;
+  int apply(const double* x_loc, double* y_loc, cudaStream_t stream) {
+    if (fn) {
+      int rc = fn(x_loc, y_loc, fn_user, stream);
+      TN_REQUIRE(rc == 0, "tn_lanczos: matvec callback failed (%d)", rc);
+      return TN_OK;
+    }
+    if (rows) {
+      TN_CHECK(comm_allgather(comm, x_loc, full, n_pad, stream));
+      return tn_effh_matvec(plan, full, y_loc, 0.0, 1.0, stream);
+    }
+    TN_CHECK(tn_effh_matvec(plan, x_loc, y_loc, 0.0, 1.0, stream));
+    if (comm) return comm_allreduce_sum(comm, y_loc, n, stream);
+    if (allreduce) {
+      int rc = allreduce(y_loc, n, allreduce_user, stream);
+      TN_REQUIRE(rc == 0, "tn_lanczos_lm1: all-reduce callback failed (%d)", rc);
+    }
+    return TN_OK;
+  }
+};
 
-extern "C" size_t tn_lanczos_workspace_bytes(long long n, int ncv) {
-  const long long m = std::min<long long>(std::max(ncv, 2), std::min<long long>(n, kMaxNcv));
-  const size_t ldv = (size_t)((n + 1) / 2 * 2);
+static size_t lanczos_ws_bytes(long long n_loc_pad, int ncv, long long full_len) {
+  const long long m = std::min<long long>(std::max(ncv, 2), kMaxNcv);
+  const size_t ldv = (size_t)((n_loc_pad + 1) / 2 * 2);
   return align_up(sizeof(double) * ldv * (size_t)(m + 2)) +
-         align_up(sizeof(double) * std::max<size_t>((size_t)(m + 2) * dot_chunks(n), (size_t)3 * 2048 * (kMaxNcv + 1))) +
-         align_up(sizeof(LanczosState)) + align_up(sizeof(unsigned)) + 1024;
+         align_up(sizeof(double) * std::max<size_t>((size_t)(m + 2) * dot_chunks(n_loc_pad), (size_t)3 * 2048 * (kMaxNcv + 1))) +
+         align_up(sizeof(LanczosState)) + align_up(sizeof(unsigned)) + align_up(sizeof(double) * (size_t)full_len) + 1024;
 }
 
-extern "C" int tn_lanczos_lm1(tn_effh_plan* plan, double tau, const double* v0, double tol, int ncv, int max_restarts,
-                              double* lambda_out, double* vec_out, int* n_matvec_out, double* resid_out,
-                              tn_allreduce_fn allreduce, void* allreduce_user, void* workspace, size_t workspace_bytes,
-                              void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  TN_REQUIRE(plan && v0 && vec_out, "tn_lanczos_lm1: null argument");
-  TN_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "tn_lanczos_lm1: workspace must be 256-byte aligned");
-  const long long n = plan_dim(plan);
-  if (workspace_bytes < tn_lanczos_workspace_bytes(n, ncv)) {
-    set_error("tn_lanczos_lm1: workspace %zu < %zu bytes", workspace_bytes, tn_lanczos_workspace_bytes(n, ncv));
+// n: global dimension; n_loc: length of this rank's slice (== n when nothing is sliced); off: its offset in the vector
+static int lanczos_core(LanczosOp& op, long long n, long long n_loc, long long off, double tau, const double* v0, double tol,
+                        int ncv, int max_restarts, const double* locked, int n_locked, long long ld_locked,
+                        double* lambda_out, double* vec_out, int* n_matvec_out, double* resid_out, void* workspace,
+                        size_t workspace_bytes, cudaStream_t stream) {
+  const bool sliced = op.rows;
+  tn_comm* comm = op.comm;
+  const long long n_store = sliced ? op.n_pad : n;  // stored length of a basis vector (the pad is zero and never written)
+  const long long full_len = sliced ? op.n_pad * comm->world : 0;
+  if (workspace_bytes < lanczos_ws_bytes(n_store, ncv, full_len)) {
+    set_error("tn_lanczos: workspace %zu < %zu bytes", workspace_bytes, lanczos_ws_bytes(n_store, ncv, full_len));
     return TN_ERR_WORKSPACE;
   }
-  TN_REQUIRE(tol >= 0 && max_restarts >= 1, "tn_lanczos_lm1: bad tol/max_restarts");
-  const int m = (int)std::min<long long>(std::max(ncv, 2), std::min<long long>(n, kMaxNcv));
-  const long long ldv = (n + 1) / 2 * 2;
+  const int m = (int)std::min<long long>(std::max(ncv, 2), std::min<long long>(n - n_locked, kMaxNcv));
+  TN_REQUIRE(m >= 1, "tn_lanczos: nothing left to solve (n = %lld, locked = %d)", n, n_locked);
+  const long long ldv = (n_store + 1) / 2 * 2;
   Carver cw(workspace, workspace_bytes);
   double* V = cw.take<double>((size_t)ldv * (m + 2));
-  double* partial = cw.take<double>(std::max<size_t>((size_t)(m + 2) * dot_chunks(n), (size_t)3 * 2048 * (kMaxNcv + 1)));
+  double* partial = cw.take<double>(std::max<size_t>((size_t)(m + 2) * dot_chunks(n_store), (size_t)3 * 2048 * (kMaxNcv + 1)));
   LanczosState* st = cw.take<LanczosState>(1);
   unsigned* counter = cw.take<unsigned>(1);
-  TN_REQUIRE(V && partial && st && counter, "tn_lanczos_lm1: workspace carve failed");
+  double* full = sliced ? cw.take<double>((size_t)full_len) : nullptr;
+  TN_REQUIRE(V && partial && st && counter && (!sliced || full), "tn_lanczos: workspace carve failed");
+  op.full = full;
   double* ytmp = V + (size_t)ldv * (m + 1);
   auto vec = [&](int j) { return V + (size_t)ldv * j; };
+  // dot products of slices are partial sums: one small all-reduce makes them global (and identical on every rank)
+  auto reduce = [&](double* dev, int count) -> int { return sliced ? comm_allreduce_sum(comm, dev, count, stream) : TN_OK; };
+  auto project_locked = [&](double* w) -> int {  // w -= Lk (Lk^T w), twice (locked vectors are orthonormal)
+    for (int pass = 0; pass < 2 && n_locked > 0; ++pass) {
+      TN_CHECK(launch_multidot(locked, ld_locked, n_locked, w, n_loc, st->lock_h, partial, counter, stream));
+      TN_CHECK(launch_multi_axpy(w, locked, ld_locked, n_locked, st->lock_h, n_loc, stream));
+    }
+    return TN_OK;
+  };
 
   TN_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), stream));
   TN_CUDA(cudaMemsetAsync(st, 0, sizeof(LanczosState), stream));
+  if (sliced) TN_CUDA(cudaMemsetAsync(V, 0, sizeof(double) * (size_t)ldv * (m + 2), stream));  // the pads travel through all-gathers
   // v_0 = v0 / |v0|
-  TN_CUDA(cudaMemcpyAsync(vec(0), v0, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
-  TN_CHECK(launch_multidot(vec(0), ldv, 1, vec(0), n, &st->nrm2, partial, counter, stream));
+  TN_CUDA(cudaMemcpyAsync(vec(0), v0 + off, sizeof(double) * n_loc, cudaMemcpyDeviceToDevice, stream));
+  TN_CHECK(project_locked(vec(0)));
+  TN_CHECK(launch_multidot(vec(0), ldv, 1, vec(0), n_loc, &st->nrm2, partial, counter, stream));
+  TN_CHECK(reduce(&st->nrm2, 1));
   lanczos_init_kernel<<<1, 1, 0, stream>>>(st);
   TN_LAUNCHED();
-  TN_CHECK(launch_scale_dev(vec(0), &st->inv_beta, n, stream));
+  TN_CHECK(launch_scale_dev(vec(0), &st->inv_beta, n_loc, stream));
 
   // fused cooperative re-orthogonalisation when the vectors are L2 resident and a slice fits the shared-memory buffer
   int fused_grid = 0, fused_slice = 0, fused_cache = 0;
   size_t fused_smem = 0;
-  if (n <= kFusedMaxN && !getenv("TNALG_NO_FUSED_ORTH")) {
+  if (!sliced && n <= kFusedMaxN && !getenv("TNALG_NO_FUSED_ORTH")) {
     const int sms = sm_count();
     // preferred: one CTA per SM with the CTA's slice of the whole basis cached in shared memory
     const int grid1 = (int)std::max<long long>(1, std::min<long long>(sms, (n + 511) / 512));
@@ -343,13 +423,21 @@ extern "C" int tn_lanczos_lm1(tn_effh_plan* plan, double tau, const double* v0, 
   for (int cycle = 0; cycle < max_restarts; ++cycle) {
     for (int j = j0; j < m; ++j) {
       double* w = vec(j + 1);
-      TN_CHECK(tn_effh_matvec(plan, vec(j), w, 0.0, 1.0, stream));
+      TN_CHECK(op.apply(vec(j), w, stream));
       ++n_matvec;
-      if (allreduce) {
-        int rc = allreduce(w, n, allreduce_user, stream);
-        TN_REQUIRE(rc == 0, "tn_lanczos_lm1: all-reduce callback failed (%d)", rc);
-      }
-      if (fused_grid > 0) {
+      TN_CHECK(project_locked(w));
+      if (sliced) {
+        // sliced basis: full CGS2 with two small all-reduces per step (h and w.w; h2 and w'.w')
+        TN_CHECK(launch_multidot(V, ldv, j + 2, w, n_loc, st->h, partial, counter, stream));
+        TN_CHECK(reduce(st->h, j + 2));
+        TN_CHECK(launch_multi_axpy(w, V, ldv, j + 1, st->h, n_loc, stream));
+        TN_CHECK(launch_multidot(V, ldv, j + 2, w, n_loc, st->h2, partial, counter, stream));
+        TN_CHECK(reduce(st->h2, j + 2));
+        TN_CHECK(launch_multi_axpy(w, V, ldv, j + 1, st->h2, n_loc, stream));
+        lanczos_finish_sharded_kernel<<<1, 1, 0, stream>>>(st, j);
+        TN_LAUNCHED();
+        TN_CHECK(launch_scale_dev(w, &st->inv_beta, n_loc, stream));
+      } else if (fused_grid > 0) {
         // one cooperative launch: CGS2, norm, scale and the alpha/beta bookkeeping of step j
         long long ldv_arg = ldv, n_arg = n;
         int j_arg = j;
@@ -378,33 +466,108 @@ extern "C" int tn_lanczos_lm1(tn_effh_plan* plan, double tau, const double* v0, 
     TN_CUDA(cudaMemcpyAsync(&hs, &st->theta, sizeof(LanczosStatus), cudaMemcpyDeviceToHost, stream));
     TN_CUDA(cudaStreamSynchronize(stream));
     if (hs.ql_fail) {
-      set_error("tn_lanczos_lm1: tridiagonal QL did not converge");
-      return TN_ERR_NOCONV;
+      // nothing has been written to the outputs: a hard error, not the soft "iteration limit" status
+      set_error("tn_lanczos: the projected tridiagonal eigenproblem did not converge (NaN/Inf in the operator or the start vector?)");
+      return TN_ERR_NUMERIC;
     }
     // Ritz vector y = V u
-    TN_CHECK(launch_combine(ytmp, V, ldv, hs.m_eff, st->u, n, stream));
-    if (hs.converged || m >= n) {
+    TN_CHECK(launch_combine(ytmp, V, ldv, hs.m_eff, st->u, n_loc, stream));
+    if (hs.converged || m >= n - n_locked) {
       status = TN_OK;
       break;
     }
     if (cycle + 1 == max_restarts) break;
     // thick restart: v_0 = y, v_1 = residual direction (old v_m), T[0,0] = theta, T[0,1] = s
-    TN_CUDA(cudaMemcpyAsync(vec(0), ytmp, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
-    TN_CUDA(cudaMemcpyAsync(vec(1), vec(m), sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
+    TN_CUDA(cudaMemcpyAsync(vec(0), ytmp, sizeof(double) * n_loc, cudaMemcpyDeviceToDevice, stream));
+    TN_CUDA(cudaMemcpyAsync(vec(1), vec(m), sizeof(double) * n_loc, cudaMemcpyDeviceToDevice, stream));
     lanczos_restart_kernel<<<1, 1, 0, stream>>>(st);
     TN_LAUNCHED();
     j0 = 1;
   }
   // normalise and return
-  TN_CHECK(launch_multidot(ytmp, ldv, 1, ytmp, n, &st->nrm2, partial, counter, stream));
+  TN_CHECK(launch_multidot(ytmp, ldv, 1, ytmp, n_loc, &st->nrm2, partial, counter, stream));
+  TN_CHECK(reduce(&st->nrm2, 1));
   lanczos_init_kernel<<<1, 1, 0, stream>>>(st);
   TN_LAUNCHED();
-  TN_CHECK(launch_scale_dev(ytmp, &st->inv_beta, n, stream));
-  TN_CUDA(cudaMemcpyAsync(vec_out, ytmp, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
+  TN_CHECK(launch_scale_dev(ytmp, &st->inv_beta, n_loc, stream));
+  if (sliced) {  // every rank receives the whole eigenvector (bit-identical on all ranks)
+    TN_CHECK(comm_allgather(comm, ytmp, full, op.n_pad, stream));
+    TN_CUDA(cudaMemcpyAsync(vec_out, full, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
+  } else {
+    TN_CUDA(cudaMemcpyAsync(vec_out, ytmp, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
+  }
   TN_CUDA(cudaStreamSynchronize(stream));
   if (lambda_out) *lambda_out = hs.lambda;
   if (resid_out) *resid_out = hs.resid;
   if (n_matvec_out) *n_matvec_out = n_matvec;
-  if (status == TN_ERR_NOCONV) set_error("tn_lanczos_lm1: not converged after %d restart cycles (residual %.3e)", max_restarts, hs.resid);
+  if (status == TN_ERR_NOCONV) set_error("tn_lanczos: not converged after %d restart cycles (residual %.3e)", max_restarts, hs.resid);
   return status;
+}
+
+}  // namespace tn
+
+using namespace tn;
+
+// slice geometry of a row-sliced plan inside a communicator: rows_per = ceil(a / world), rank r owns rows [r*rows_per, ...)
+static int sliced_geometry(tn_effh_plan* plan, tn_comm* comm, long long* n_pad) {
+  const long long n = plan_dim(plan), n_out = plan_slice_len(plan), off = plan_slice_offset(plan);
+  int rb = 0, rc = 0;
+  tn_effh_plan_rows(plan, &rb, &rc);
+  TN_REQUIRE(comm && comm->world >= 1, "tn_lanczos_lm1: a row-sliced plan needs a communicator");
+  const long long per_row = n_out / rc;                 // d * b
+  const long long a = n / per_row;
+  const long long rows_per = (a + comm->world - 1) / comm->world;
+  TN_REQUIRE((long long)rb == rows_per * comm->rank && rc == std::min<long long>(rows_per, a - rb) && off == rb * per_row,
+             "tn_lanczos_lm1: plan rows [%d, %d) do not match rank %d of %d (rows per rank %lld)", rb, rb + rc, comm->rank,
+             comm->world, rows_per);
+  *n_pad = rows_per * per_row;
+  return TN_OK;
+}
+
+extern "C" size_t tn_lanczos_workspace_bytes(long long n, int ncv) { return lanczos_ws_bytes(n, ncv, 0); }
+
+extern "C" size_t tn_lanczos_workspace_bytes_sharded(const tn_effh_plan* plan, const tn_comm* comm, int ncv) {
+  if (!plan) return 0;
+  if (!plan_is_rows(plan) || !comm) return lanczos_ws_bytes(plan_dim(plan), ncv, 0);
+  long long n_pad = 0;
+  if (sliced_geometry(const_cast<tn_effh_plan*>(plan), const_cast<tn_comm*>(comm), &n_pad) != TN_OK) return 0;
+  return lanczos_ws_bytes(n_pad, ncv, n_pad * comm->world);
+}
+
+extern "C" int tn_lanczos_lm1(tn_effh_plan* plan, double tau, const double* v0, double tol, int ncv, int max_restarts,
+                              double* lambda_out, double* vec_out, int* n_matvec_out, double* resid_out,
+                              tn_allreduce_fn allreduce, void* allreduce_user, tn_comm* comm, void* workspace,
+                              size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TN_REQUIRE(plan && v0 && vec_out, "tn_lanczos_lm1: null argument");
+  TN_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "tn_lanczos_lm1: workspace must be 256-byte aligned");
+  TN_REQUIRE(tol >= 0 && max_restarts >= 1, "tn_lanczos_lm1: bad tol/max_restarts");
+  TN_REQUIRE(!(allreduce && comm), "tn_lanczos_lm1: pass either an all-reduce callback or a communicator, not both");
+  LanczosOp op;
+  op.plan = plan; op.allreduce = allreduce; op.allreduce_user = allreduce_user; op.comm = comm;
+  op.n = plan_dim(plan);
+  long long n_loc = op.n, off = 0;
+  if (plan_is_rows(plan)) {
+    TN_CHECK(sliced_geometry(plan, comm, &op.n_pad));
+    op.rows = true;
+    n_loc = plan_slice_len(plan);
+    off = plan_slice_offset(plan);
+  }
+  return lanczos_core(op, op.n, n_loc, off, tau, v0, tol, ncv, max_restarts, nullptr, 0, 0, lambda_out, vec_out, n_matvec_out,
+                      resid_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int tn_lanczos_generic(tn_matvec_fn matvec, void* user, long long n, double tau, const double* v0, double tol, int ncv,
+                                  int max_restarts, const double* locked, int n_locked, long long ld_locked, double* lambda_out,
+                                  double* vec_out, int* n_matvec_out, double* resid_out, void* workspace, size_t workspace_bytes,
+                                  void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  TN_REQUIRE(matvec && v0 && vec_out && n > 0, "tn_lanczos_generic: null argument");
+  TN_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "tn_lanczos_generic: workspace must be 256-byte aligned");
+  TN_REQUIRE(tol >= 0 && max_restarts >= 1, "tn_lanczos_generic: bad tol/max_restarts");
+  TN_REQUIRE(n_locked >= 0 && n_locked <= kMaxNcv && (n_locked == 0 || (locked && ld_locked >= n)), "tn_lanczos_generic: bad locked vectors");
+  LanczosOp op;
+  op.fn = matvec; op.fn_user = user; op.n = n;
+  return lanczos_core(op, n, n, 0, tau, v0, tol, ncv, max_restarts, locked, n_locked, ld_locked, lambda_out, vec_out,
+                      n_matvec_out, resid_out, workspace, workspace_bytes, stream);
 }

@@ -14,6 +14,9 @@ void set_error(const char* fmt, ...) {
   g_err = buf;
 }
 
+static std::atomic<int> g_deterministic{0};
+bool deterministic_mode() { return g_deterministic.load() != 0; }
+
 int sm_count() {
   static int cached = 0;
   if (cached == 0) {
@@ -28,7 +31,11 @@ int sm_count() {
 }  // namespace tn
 
 extern "C" const char* tn_last_error(void) { return tn::g_err.c_str(); }
-extern "C" int tn_version(void) { return 100; }
+extern "C" int tn_version(void) { return 200; }
+extern "C" int tn_set_deterministic(int on) {
+  int old = tn::g_deterministic.exchange(on ? 1 : 0);
+  return old;
+}
 extern "C" long long tn_launch_count(void) { return tn::g_launches.load(); }
 extern "C" void tn_launch_count_reset(void) { tn::g_launches.store(0); }
 

@@ -221,7 +221,7 @@ extern "C" int tn_lincomb(double* out, long long n, int n_terms, const double* c
 }
 
 extern "C" int tn_apply_site_op(double* out, const double* T, int a, int d, int b, const double* op, void* stream_) {
-  TN_REQUIRE(out && T && op && a > 0 && b > 0 && d >= 1 && d <= kMaxD, "tn_apply_site_op: bad arguments");
+  TN_REQUIRE(out && T && op && a > 0 && b > 0 && d >= 1 && d <= kMaxPhys, "tn_apply_site_op: bad arguments");
   TN_REQUIRE(out != T, "tn_apply_site_op: in-place not supported");
   SiteOp o{};
   for (int i = 0; i < d * d; ++i) o.m[i] = op[i];

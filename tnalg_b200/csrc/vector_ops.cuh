@@ -5,7 +5,7 @@
 namespace tn {
 
 struct SiteOp {
-  double m[kMaxD * kMaxD];
+  double m[kMaxPhys * kMaxPhys];
 };
 
 // out[a,s,b] = c_id * x[a,s,b] + c_op * sum_s' op[s,s'] x[a,s',b]     (x is (a,d,b) C-order)

@@ -117,7 +117,7 @@ class EnvCache:
         self.rv = length   # right blocks of bonds rv..L are valid
         self.n_bond_moves = 0
         self.merge_crossing = True   # False: one GEMM link per crossing term, the reference's literal '1_0_1' list
-        self.dist = None             # torch.distributed module when the outgoing operators of a bond move are sharded over ranks
+        self.comm = None             # backend communicator when the outgoing operators of a bond move are sharded over ranks
 
     def invalidate_site(self, n):
         """tensor n changed: left blocks of bonds > n and right blocks of bonds <= n are stale"""
@@ -137,21 +137,25 @@ class EnvCache:
     # ---- bond moves ----
     def _env_update(self, direction, T, outputs):
         """tn_env_update for every outgoing operator of a bond; with several ranks each rank computes the operators
-        j = rank (mod world) and broadcasts them, so all ranks end up with bit-identical blocks (one writer per operator)"""
-        dist = self.dist
-        if dist is None or dist.get_world_size() == 1 or len(outputs) < 2:
+        j = rank (mod world) and all of them are exchanged in ONE grouped broadcast, so all ranks end up with bit-identical
+        blocks (one writer per operator)"""
+        comm = self.comm
+        e_dim = T.shape[2] if direction == 0 else T.shape[0]
+        if comm is None or comm.world == 1 or len(outputs) < 2 or e_dim < 64:
             return self.be.env_update(direction, T, outputs)
-        rank, world = dist.get_rank(), dist.get_world_size()
-        mine = [j for j in range(len(outputs)) if j % world == rank]
+        rank, world = comm.rank, comm.world
+        # heaviest outputs first (the H block carries several links), dealt round-robin
+        order = sorted(range(len(outputs)), key=lambda j: -len(outputs[j]))
+        owner = {j: i % world for i, j in enumerate(order)}
+        mine = [j for j in range(len(outputs)) if owner[j] == rank]
         res = [None] * len(outputs)
         if mine:
             for j, mat in zip(mine, self.be.env_update(direction, T, [outputs[j] for j in mine])):
                 res[j] = mat
-        e_dim = T.shape[2] if direction == 0 else T.shape[0]
         for j in range(len(outputs)):
             if res[j] is None:
                 res[j] = self.be.empty(e_dim, e_dim)
-            dist.broadcast(res[j], src=j % world)
+        comm.broadcast_many(res, [owner[j] for j in range(len(outputs))])
         return res
 
     def _lincomb(self, block, pairs):
@@ -330,24 +334,24 @@ class EnvCache:
         g['n_x_reference'] = len(cross)
         return g
 
-    def plan_two_site(self, p, mps, rank=0, world=1):
+    def plan_two_site(self, p, mps, rank=0, world=1, rows=None):
         self.ensure(p, mps, width=2)
         a, d, _ = mps[p].shape
         b = mps[p + 1].shape[2]
         g = self.groups_two_site(p, d)
         plan = self.be.effh_plan((a, d * d, b), g['HL'], g['HR'], g['M'], g['LS'], g['ls_ops'], g['RS'], g['rs_ops'],
-                                 g['XL'], g['XR'], g['x_coeff'], rank=rank, world=world)
+                                 g['XL'], g['XR'], g['x_coeff'], rank=rank, world=world, **({'rows': rows} if rows is not None else {}))
         kl = (1 if g['HL'] is not None else 0) + len(g['LS'])
         kr = (1 if g['HR'] is not None else 0) + len(g['RS'])
         plan.flops_algorithmic = 2.0 * a * d * d * b * (a * (kl + g['n_x_reference']) + b * (kr + g['n_x_reference']))
         return plan
 
-    def plan(self, p, mps, rank=0, world=1):
+    def plan(self, p, mps, rank=0, world=1, rows=None):
         self.ensure(p, mps)
         a, d, b = mps[p].shape
         g = self.groups(p, d)
         plan = self.be.effh_plan((a, d, b), g['HL'], g['HR'], g['M'], g['LS'], g['ls_ops'], g['RS'], g['rs_ops'],
-                                 g['XL'], g['XR'], g['x_coeff'], rank=rank, world=world)
+                                 g['XL'], g['XR'], g['x_coeff'], rank=rank, world=world, **({'rows': rows} if rows is not None else {}))
         # algorithmic flop of one matvec = the reference's own grouping, whatever the kernel executes
         kl = (1 if g['HL'] is not None else 0) + len(g['LS'])
         kr = (1 if g['HR'] is not None else 0) + len(g['RS'])

@@ -1,9 +1,9 @@
 """Host-side operator layer: torch CUDA tensors in, C-ABI calls out.
 
 `backend()` returns the process-wide CudaBackend.  Every method maps 1:1 onto an entry point of
-include/tnalg_b200.h; torch is used for device memory, streams and (multi-GPU) torch.distributed only.
-The one library call kept in round 1 is the QR factorisation of gauge moves (torch.linalg.qr -> cuSOLVER geqrf),
-see DESIGN.md; everything else runs in libtnalg_b200.so.
+include/tnalg_b200.h; torch is used for device memory, streams and the bootstrap of the multi-GPU communicator
+(torch.distributed carries the 128-byte NCCL id once; every collective on the data path is issued by the library).
+There is no library math on the path: QR, SVD, eigh, Lanczos and all contractions run in libtnalg_b200.so.
 """
 import ctypes as C
 
@@ -20,12 +20,6 @@ def backend():
     if _backend is None:
         _backend = CudaBackend()
     return _backend
-
-
-def set_backend(b):
-    """Dependency-injection hook used by the CPU unit tests of the host logic (tests/cpu_backend.py)."""
-    global _backend
-    _backend = b
 
 
 def _ptr(t):
@@ -49,12 +43,16 @@ class EffHPlan:
         L.check(be.lib.tn_effh_plan_flops(handle, C.byref(alg), C.byref(ex)))
         self.flops_algorithmic, self.flops_executed = alg.value, ex.value
         self.uses_tma = int(be.lib.tn_effh_plan_uses_tma(handle))  # bit 0 left stage, bit 1 right stage
+        rb, rc = C.c_int(), C.c_int()
+        self.rows = be.lib.tn_effh_plan_rows(handle, C.byref(rb), C.byref(rc)) == 1
+        self.row_begin, self.row_count = rb.value, rc.value
 
     def matvec(self, psi, c_id=0.0, c_h=1.0, out=None):
         """out = c_id*psi + c_h*H_eff psi; (c_id, c_h) = (1, -tau) is the reference handle (MPSClass.py:755-776)."""
         be = self._be
         psi = psi.contiguous()
-        out = torch.empty_like(psi) if out is None else out
+        if out is None:   # a row-sliced plan reads the full psi and returns its (row_count, d, b) slice
+            out = be.empty(self.row_count, *self.shape[1:]) if self.rows else torch.empty_like(psi)
         L.check(be.lib.tn_effh_matvec(self._handle, _ptr(psi), _ptr(out), float(c_id), float(c_h), be.stream()))
         return out
 
@@ -97,8 +95,47 @@ def preconditioned_svd(A, k, qr, jacobi, mm_nn, mm_nt):
     return U, S, Vt
 
 
+class Comm:
+    """Handle on the in-library communicator (tn_comm): rank, world and the stream-ordered collectives the hot path needs.
+    Created once per process by CudaBackend.comm(); torch.distributed only carries the 128-byte NCCL id (bootstrap)."""
+
+    def __init__(self, be, handle, rank, world):
+        self._be, self._handle, self.rank, self.world = be, handle, rank, world
+
+    def allreduce(self, t):
+        L.check(self._be.lib.tn_comm_allreduce_sum(self._handle, _ptr(t), t.numel(), self._be.stream()))
+        return t
+
+    def broadcast(self, t, src=0):
+        self.broadcast_many([t], [src])
+        return t
+
+    def broadcast_many(self, tensors, roots):
+        """one grouped NCCL launch for all the outgoing operators of a sharded environment update"""
+        n = len(tensors)
+        if n == 0:
+            return
+        L.check(self._be.lib.tn_comm_broadcast_many(self._handle, (C.c_void_p * n)(*[t.data_ptr() for t in tensors]),
+                                                    (C.c_longlong * n)(*[t.numel() for t in tensors]),
+                                                    (C.c_int * n)(*[int(r) for r in roots]), n, self._be.stream()))
+
+    def collectives(self):
+        return int(self._be.lib.tn_comm_collectives(self._handle))
+
+    def destroy(self):
+        if self._handle is not None:
+            self._be.lib.tn_comm_destroy(self._handle)
+            self._handle = None
+
+
 class CudaBackend:
     name = 'cuda'
+    # multi-GPU decomposition of a local eigenproblem: 'rows' = every rank computes a row slice of H|psi> for all terms and
+    # keeps a slice of the Krylov basis (all-gather per step); 'terms' = the coupling-term links are dealt round-robin and the
+    # partial H|psi> is all-reduced (the decomposition SURVEY.md 8e names)
+    shard_mode = 'rows'
+    shard_min_rows = 16      # a rank needs at least this many rows of the (a, d*b) output, else the site is solved replicated
+    shard_min_n = 1 << 14    # ... and the vector at least this many elements
 
     def __init__(self, device=None):
         self.lib = L.load()
@@ -112,6 +149,33 @@ class CudaBackend:
         self._ws = {}
         self._scalars = torch.zeros(4096, dtype=torch.float64, device=self.device)
         self._scalar_pos = 0
+        self._comm = None
+
+    # ---- multi-GPU communicator ----
+    def comm(self):
+        """the library communicator over the ranks of torch.distributed (None for a single process).  The NCCL unique id is
+        created by rank 0 (tn_comm_unique_id) and broadcast once through torch.distributed; the communicator itself and every
+        collective issued through it live in libtnalg_b200.so."""
+        if self._comm is not None:
+            return self._comm
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return None
+        rank, world = dist.get_rank(), dist.get_world_size()
+        ident = C.create_string_buffer(128)
+        if rank == 0:
+            L.check(self.lib.tn_comm_unique_id(ident))
+        box = [bytes(ident.raw)]
+        dist.broadcast_object_list(box, src=0)
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(self.lib.tn_comm_init_rank(C.byref(handle), box[0], rank, world))
+        self._comm = Comm(self, handle, rank, world)
+        return self._comm
+
+    def set_deterministic(self, on=True):
+        """bit-reproducible kernels (no stream-K split, no FP64-atomic tile combination, no concurrent matvec stages)"""
+        return bool(self.lib.tn_set_deterministic(1 if on else 0))
 
     # ---- memory helpers ----
     def stream(self):
@@ -235,8 +299,21 @@ class CudaBackend:
         return self.site_op(T, mat.T.cpu().numpy())
 
     # ---- a1/a2: effective Hamiltonian ----
+    def shard_rows(self, a, d, b, rank, world):
+        """(row_begin, row_count) of this rank's slice of the (a, d*b) output, or None when the site is too small to slice
+        (every rank then solves the whole problem; rows_per = ceil(a / world) is what tn_lanczos_lm1 expects)"""
+        if world <= 1 or self.shard_mode != 'rows':
+            return None
+        rows_per = -(-a // world)
+        last = a - rows_per * (world - 1)
+        if last < min(self.shard_min_rows, rows_per) or rows_per < self.shard_min_rows or a * d * b < self.shard_min_n:
+            return None
+        return rank * rows_per, min(rows_per, a - rank * rows_per)
+
     def effh_plan(self, shape, HL=None, HR=None, M=None, LS=(), ls_ops=(), RS=(), rs_ops=(), XL=(), XR=(), x_coeff=(),
-                  rank=0, world=1):
+                  rank=0, world=1, rows=None):
+        """rows = (row_begin, row_count): a row-sliced plan (tn_effh_plan_create_rows); otherwise rank/world deal the links
+        round-robin (term sharding) and (0, 1) is the full operator"""
         a, d, b = shape
         n_ls, n_rs, n_x = len(LS), len(RS), len(XL)
         keep = [t.contiguous() if t is not None else None for t in [HL, HR, *LS, *RS, *XL, *XR]]
@@ -251,26 +328,61 @@ class CudaBackend:
             return (C.c_void_p * max(len(ts), 1))(*[t.data_ptr() for t in ts]) if ts else None
 
         Mp = _op_array([M], d) if M is not None else None
-        L.check(self.lib.tn_effh_plan_create(
+        create, tail = (self.lib.tn_effh_plan_create, (rank, world)) if rows is None else (self.lib.tn_effh_plan_create_rows, tuple(rows))
+        L.check(create(
             C.byref(handle), a, d, b, _ptr(HLc), _ptr(HRc), Mp, n_ls, parr(LSc), _op_array(ls_ops, d) if n_ls else None,
             n_rs, parr(RSc), _op_array(rs_ops, d) if n_rs else None, n_x, parr(XLc), parr(XRc),
-            (C.c_double * max(n_x, 1))(*[float(c) for c in x_coeff]) if n_x else None, rank, world, _ptr(ws), ws.numel(),
+            (C.c_double * max(n_x, 1))(*[float(c) for c in x_coeff]) if n_x else None, int(tail[0]), int(tail[1]), _ptr(ws), ws.numel(),
             self.stream()))
         return EffHPlan(self, handle, ws, (a, d, b), keep)
 
     # ---- a8: eigensolver ----
-    def lanczos(self, plan, tau, v0, tol, ncv=20, max_restarts=1000, allreduce=None):
-        """dominant eigenpair of (1 - tau*H_eff): (lambda, vector, n_matvec, residual, converged)."""
+    def lanczos(self, plan, tau, v0, tol, ncv=20, max_restarts=1000, comm=None, allreduce=None):
+        """dominant eigenpair of (1 - tau*H_eff): (lambda, vector, n_matvec, residual, converged).
+        comm: the library communicator when the plan is row-sliced or term-sharded (collectives issued by the library);
+        allreduce: a host callback for term-sharded plans instead (kept for callers that bring their own collective)."""
         v0 = v0.contiguous().reshape(-1)
         n = v0.numel()
-        nbytes = self.lib.tn_lanczos_workspace_bytes(n, ncv)
+        ch = comm._handle if comm is not None else None
+        nbytes = self.lib.tn_lanczos_workspace_bytes_sharded(plan._handle, ch, int(ncv)) if ch is not None else \
+            self.lib.tn_lanczos_workspace_bytes(n, ncv)
         ws = self.workspace('lanczos', nbytes)
         out = torch.empty_like(v0)
         lam, resid, nmv = C.c_double(), C.c_double(), C.c_int()
         cb = L.ALLREDUCE_FN(allreduce) if allreduce is not None else C.cast(None, L.ALLREDUCE_FN)
         st = self.lib.tn_lanczos_lm1(plan._handle, float(tau), _ptr(v0), float(tol), int(ncv), int(max_restarts),
-                                     C.byref(lam), _ptr(out), C.byref(nmv), C.byref(resid), cb, None, _ptr(ws),
+                                     C.byref(lam), _ptr(out), C.byref(nmv), C.byref(resid), cb, None, ch, _ptr(ws),
                                      ws.numel(), self.stream())
+        if st not in (0, -4):   # -4 (iteration limit) still writes the best Ritz pair; everything else is an error
+            L.check(st)
+        return lam.value, out, nmv.value, resid.value, st == 0
+
+    def lanczos_generic(self, matvec, n, tau, v0, tol, ncv=20, max_restarts=1000, locked=None):
+        """the same device-resident solver for a caller-supplied operator: matvec(x, y) receives two float64 device tensors of
+        length n (aliases of the Krylov workspace) and must write y = H x.  locked: (n_locked, n) tensor of orthonormal vectors
+        the search stays orthogonal to (deflation)."""
+        v0 = v0.contiguous().reshape(-1)
+        nbytes = self.lib.tn_lanczos_workspace_bytes(n, ncv)
+        ws = self.workspace('lanczos', nbytes)
+        out = torch.empty_like(v0)
+        lam, resid, nmv = C.c_double(), C.c_double(), C.c_int()
+        err = []
+
+        def cb(xp, yp, user, stream):
+            try:
+                matvec(_alias(xp, n, self.device), _alias(yp, n, self.device))
+                return 0
+            except Exception as e:  # the C side turns the status into TN_ERR_INVALID; keep the Python error for the caller
+                err.append(e)
+                return 1
+        n_locked = 0 if locked is None else int(locked.shape[0])
+        if n_locked:
+            locked = locked.contiguous()
+        st = self.lib.tn_lanczos_generic(L.MATVEC_FN(cb), None, n, float(tau), _ptr(v0), float(tol), int(ncv), int(max_restarts),
+                                         _ptr(locked) if n_locked else None, n_locked, n if n_locked else 0, C.byref(lam), _ptr(out),
+                                         C.byref(nmv), C.byref(resid), _ptr(ws), ws.numel(), self.stream())
+        if err:
+            raise err[0]
         if st not in (0, -4):
             L.check(st)
         return lam.value, out, nmv.value, resid.value, st == 0
@@ -322,11 +434,87 @@ class CudaBackend:
         return U, S, Vt
 
     def qr(self, A):
-        """thin QR of gauge moves (np.linalg.qr at TensorBasicModule.py:342-345).  Round 1: cuSOLVER via torch."""
-        return torch.linalg.qr(A, mode='reduced')
+        """thin Householder QR (np.linalg.qr at TensorBasicModule.py:342-345): A (m,n) -> Q (m,k), R (k,n) -- tn_qr_householder"""
+        A = A.contiguous()
+        m, n = A.shape
+        k = min(m, n)
+        Q, R = self.empty(m, k), self.empty(k, n)
+        ws = self.workspace('qr', self.lib.tn_qr_workspace_bytes(m, n))
+        L.check(self.lib.tn_qr_householder(_ptr(A), m, n, 0, _ptr(Q), 0, _ptr(R), _ptr(ws), ws.numel(), self.stream()))
+        return Q, R
+
+    def qr_tensor(self, T, left2right):
+        """the QR gauge move on a site tensor (a,d,b) without materialising a transposed matricisation:
+        left2right: T.reshape(a*d, b) = Q R -> (Q (a,d,k), R (k,b));  else T.reshape(a, d*b)^T = Q R -> (Q^T (k,d,b), R (k,a))"""
+        T = T.contiguous()
+        a, d, b = T.shape
+        if left2right:
+            k = min(a * d, b)
+            Q, R = self.empty(a, d, k), self.empty(k, b)
+            ws = self.workspace('qr', self.lib.tn_qr_workspace_bytes(a * d, b))
+            L.check(self.lib.tn_qr_l2r(_ptr(T), a, d, b, _ptr(Q), _ptr(R), _ptr(ws), ws.numel(), self.stream()))
+        else:
+            k = min(a, d * b)
+            Q, R = self.empty(k, d, b), self.empty(k, a)
+            ws = self.workspace('qr', self.lib.tn_qr_workspace_bytes(d * b, a))
+            L.check(self.lib.tn_qr_r2l(_ptr(T), a, d, b, _ptr(Q), _ptr(R), _ptr(ws), ws.numel(), self.stream()))
+        return Q, R
+
+    def eigh(self, A):
+        """symmetric eigenproblem on the Jacobi kernels (tn_eigh_jacobi): ascending eigenvalues, eigenvectors in columns"""
+        A = A.contiguous()
+        n = A.shape[0]
+        w, V = self.empty(n), self.empty(n, n)
+        ws = self.workspace('eigh', self.lib.tn_eigh_workspace_bytes(n))
+        sweeps = C.c_int()
+        L.check(self.lib.tn_eigh_jacobi(_ptr(A), n, _ptr(w), _ptr(V), C.byref(sweeps), _ptr(ws), ws.numel(), self.stream()))
+        return w, V
+
+    # ---- (f)4: exact diagonalisation on the full d^L space ----
+    def _ed_args(self, couplings, hamilts, d):
+        couplings = np.asarray(couplings, dtype=int).reshape(-1, 3)
+        nt, nh = couplings.shape[0], len(hamilts)
+        hs = np.concatenate([np.asarray(np.real(h), dtype=float).reshape(-1) for h in hamilts])
+        if hs.size != nh * d ** 4:
+            raise ValueError('two-site Hamiltonians must be (d^2, d^2)')
+        arr = lambda col: (C.c_int * nt)(*[int(x) for x in couplings[:, col]])  # noqa: E731
+        return nt, nh, arr(0), arr(1), arr(2), (C.c_double * hs.size)(*hs)
+
+    def ed_apply(self, v, L_sites, d, couplings, hamilts, c_id=1.0, c_h=-1e-4):
+        """EDbasic.project_all_hamilt (library/EDspinClass.py:69-77): c_id*v + c_h*sum_n h[c_n](p1_n, p2_n) v"""
+        v = v.contiguous().reshape(-1)
+        nt, nh, p1, p2, hi, hs = self._ed_args(couplings, hamilts, d)
+        out = torch.empty_like(v)
+        ws = self.workspace('ed', self.lib.tn_ed_workspace_bytes(L_sites, d, nt, nh, 2))
+        L.check(self.lib.tn_ed_apply(_ptr(out), _ptr(v), L_sites, d, nt, p1, p2, hi, hs, nh, float(c_id), float(c_h), _ptr(ws),
+                                     ws.numel(), self.stream()))
+        return out
+
+    def ed_ground_state(self, v0, L_sites, d, couplings, hamilts, tau=1e-4, tol=1e-12, ncv=20, max_restarts=2000):
+        """exact_ground_state (algorithms/ExactDiagonalizationAlgo.py:12-24): dominant eigenpair of 1 - tau*H on d^L"""
+        v0 = v0.contiguous().reshape(-1)
+        nt, nh, p1, p2, hi, hs = self._ed_args(couplings, hamilts, d)
+        out = torch.empty_like(v0)
+        ws = self.workspace('ed', self.lib.tn_ed_workspace_bytes(L_sites, d, nt, nh, ncv))
+        lam, resid, nmv = C.c_double(), C.c_double(), C.c_int()
+        st = self.lib.tn_ed_ground_state(L_sites, d, nt, p1, p2, hi, hs, nh, float(tau), _ptr(v0), float(tol), int(ncv),
+                                         int(max_restarts), C.byref(lam), _ptr(out), C.byref(nmv), C.byref(resid), _ptr(ws),
+                                         ws.numel(), self.stream())
+        if st not in (0, -4):
+            L.check(st)
+        return lam.value, out, nmv.value, resid.value, st == 0
 
     def scale_diag_rows(self, S, Vt):
         return S[:, None] * Vt
 
     def norm(self, x):
         return float(torch.linalg.vector_norm(x))
+
+
+def _alias(ptr, count, device):
+    """torch view of `count` float64 values at device address `ptr` (operands handed to a matvec callback)"""
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {'shape': (int(count),), 'typestr': '<f8', 'data': (int(ptr), False), 'version': 2}
+    return torch.as_tensor(h, device=device)
