@@ -9,8 +9,9 @@ A step is ONE full DMRG sweep (2L-2 local updates: environments, device Lanczos,
 model on the 6x6 open square lattice at chi = 1024 (BASELINE configs[3], the configuration the metric is quoted on;
 it fits one GPU).  `value` is matvecs/s over the timed sweeps with the MPS resident in HBM; `e2e` is the same metric
 through the drop-in API with the MPS starting in pinned host memory and the results (observables + tensors) read back
-every step.  For N > 1 the coupling-term links of every matvec are sharded over the ranks (strong scaling) with one
-NCCL all-reduce of H|psi> per Lanczos step.
+every step.  For N > 1 every local eigenproblem is sharded over the ranks (strong scaling): each rank computes a row slice of
+H|psi> for all coupling terms and keeps a slice of the Krylov basis; the exchange step is one NCCL all-gather per Lanczos step
+issued by the library (--shard terms: the term-sharded variant with one all-reduce of H|psi>).
 """
 import argparse
 import json
@@ -199,32 +200,111 @@ def default_matvecs_per_site(para, counts):
     return per
 
 
+def config_block(para, workload, world, counts, ncv=20):
+    """the `config` object both arms print (identical keys and values for the same workload / N)"""
+    widest = max(counts, key=lambda c: c['flop'])
+    L = para['l']
+    return {'workload': workload, 'L': L, 'chi': para['chi'], 'd': int(para['d']), 'terms': int(para['index2'].shape[0]),
+            'eigs_tol': para['eigs_tol'], 'ncv': ncv, 'step': 'one full sweep = %d local updates' % (2 * L - 2),
+            'l2': 'inputs larger than L2 (environment blocks of one matvec: %.0f MiB)'
+                  % ((widest['kl'] + widest['nx']) * widest['a'] ** 2 * 8 / 2 ** 20 + (widest['kr'] + widest['nx']) * widest['b'] ** 2 * 8 / 2 ** 20),
+            'parallelism': 'local problems sharded over %d GPU(s)' % world}
+
+
+def cpu_local_update_sample(para, counts):
+    """ONE local update of the reference path at the widest cut on the host cores, with the oracle port (numpy BLAS + scipy ARPACK):
+    the environment work a cached reference does per update -- (L-1) identity transfers of update_all_effective_id
+    (MPSClass.py:491-502) plus one transfer per live operator of the bond (get_effective_operators_*, :252-304) -- and
+    eigsh(LinearOperator(handle), k=1, which='LM', tol=eigs_tol) on the matvec handle (MPSClass.py:755-776,801-805) with synthetic
+    environment blocks of the real shapes.  Returns seconds, handle calls and the flop rate."""
+    from scipy.sparse.linalg import LinearOperator, eigsh
+    from oracle import dmrg_oracle as orc
+    widest = max(counts, key=lambda c: c['flop'])
+    a, b, d = widest['a'], widest['b'], para['d']
+    rng = np.random.RandomState(0)
+
+    def sym(n):
+        g = rng.randn(n, n) / np.sqrt(n)
+        return (g + g.T) / 2
+    env = {}
+    ops = [np.real(o) for o in para['op'][:6]]
+    if widest['kl'] > 0:
+        env['1_0_0'] = sym(a)
+        for s in (3, 4, 5)[:widest['kl'] - 1]:
+            env['1_%d_0' % s] = sym(a)
+    if widest['kr'] > 0:
+        env['0_0_1'] = sym(b)
+        for s in (3, 4, 5)[:widest['kr'] - 1]:
+            env['0_%d_1' % s] = sym(b)
+    if widest['nx'] > 0:
+        env['1_0_1'] = [[0.5, sym(a), sym(b)] for _ in range(widest['nx'])]
+    A = orc.OracleMps(2, d, 2, ops + [np.zeros((d, d))], mps=[np.zeros((1, d, 2)), np.zeros((2, d, 1))])
+    T = rng.randn(a, d, b) / np.sqrt(a * d)
+    E = sym(a)
+    n_transfers = (para['l'] - 1) + 3 * int(round(np.sqrt(para['l']))) + 1   # identity chain + live operators (3W+1)
+    x = rng.randn(a * d * b)
+    x /= np.linalg.norm(x)
+    calls = [0]
+
+    def handle(v):
+        calls[0] += 1
+        return A.apply_handle(v, env, (a, d, b), para['tau'])
+    t0 = time.time()
+    for _ in range(n_transfers):
+        orc.transfer_l2r(T, None, E)
+    t_env = time.time() - t0
+    t1 = time.time()
+    eigsh(LinearOperator((x.size, x.size), matvec=handle, dtype=float), k=1, which='LM', v0=x, tol=para['eigs_tol'])
+    t_eig = time.time() - t1
+    flop = calls[0] * widest['flop'] + n_transfers * 2.0 * a * d * b * (a + b)
+    return dict(t=t_env + t_eig, t_env=t_env, t_eig=t_eig, calls=calls[0], n_transfers=n_transfers, flop_rate=flop / (t_env + t_eig),
+                mv_rate_flops=calls[0] * widest['flop'] / (t_env + t_eig), a=a, b=b, kl=widest['kl'], kr=widest['kr'], nx=widest['nx'])
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([int(i.get('num_threads', 1)) for i in threadpool_info()] + [1])
+    except Exception:
+        return None
+
+
 def run_reference_arm(args, para, workload):
+    """CPU arm: the reference's own path (oracle port: numpy BLAS + scipy ARPACK, all host threads) on the same workload.
+    A full chi = 1024 sweep is ~6 minutes of 16-32 cores, so every step times ONE complete local update at the widest cut
+    (environment transfers + eigsh on the matvec handle) and the sweep value is extrapolated by sum_p F_mv(p); at most
+    `max_measured` steps are really executed so that the run ends within a few minutes."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     counts = site_counts(para)
-    threads = os.cpu_count()
     per_site = default_matvecs_per_site(para, counts)
-    vals, times = [], []
-    for step in range(args.warmup + args.steps):
-        s = cpu_matvec_sample(para, counts, budget_s=8.0, max_calls=1)
-        v, t = cpu_sweep_estimate(counts, s, per_site)
-        if step >= args.warmup:
-            vals.append(v)
-            times.append(t)
+    total_mv = sum(per_site)
+    sweep_flop = sum(n * c['flop'] for n, c in zip(per_site, counts))
+    max_measured = 4
+    vals, times, s = [], [], None
+    for step in range(min(args.warmup, 1) + min(args.steps, max_measured)):
+        s = cpu_local_update_sample(para, counts)
+        if step >= min(args.warmup, 1):
+            t_sweep = sweep_flop / s['mv_rate_flops']        # matvec flop of the sweep at the rate of a whole local update
+            vals.append(total_mv / t_sweep)
+            times.append(t_sweep)
     value = float(np.mean(vals))
-    sample = ('per step: 1 call of the reference matvec handle (oracle port, numpy BLAS) at the widest site '
-              'a=b=%d K_L=%d K_R=%d n_x=%d; sweep matvecs/s extrapolated by sum_p F_mv(p) over %d matvecs'
-              % (s['a'], s['kl'], s['kr'], s['nx'], sum(per_site)))
+    threads = blas_threads() or os.cpu_count()
+    sample = ('%d of %d steps measured, each ONE full local update of the reference path at the widest cut a=b=%d K_L=%d K_R=%d n_x=%d '
+              '(oracle port; %d environment transfers %.2f s + scipy eigsh with %d handle calls %.2f s, %.0f GFLOP/s); sweep matvecs/s '
+              'extrapolated by sum_p F_mv(p) over %d matvecs'
+              % (len(vals), args.steps, s['a'], s['kl'], s['kr'], s['nx'], s['n_transfers'], s['t_env'], s['calls'], s['t_eig'],
+                 s['flop_rate'] / 1e9, total_mv))
     line = {'impl': 'reference', 'metric': 'dmrg_sweep_matvecs_per_s', 'value': value, 'unit': 'matvec/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': float(np.mean(times)) * 1e3, 'higher_is_better': True,
             'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': workload, 'L': para['l'], 'chi': para['chi'], 'd': int(para['d']), 'terms': int(para['index2'].shape[0]),
-                       'eigs_tol': para['eigs_tol'], 'ncv': 20, 'step': 'one full sweep = %d local updates' % (2 * para['l'] - 2),
-                       'extrapolated': True},
+            'config': config_block(para, workload, args.gpus, counts),
             'cpu_baseline': {'value': value, 'unit': 'matvec/s', 'cores': threads, 'kind': 'port', 'sample': sample,
-                             'gflops_widest': s['flop_rate'] / 1e9},
+                             'extrapolated': True, 'host_cpus': os.cpu_count(),
+                             'omp_num_threads_env': os.environ.get('OMP_NUM_THREADS'),
+                             'note': 'kind=port: the unmodified reference (oracle/ref_shim.py) needs /root/reference, which does not '
+                                     'exist on the GPU box; the port is pinned to it by tests/golden'},
             'e2e': {'value': value, 'unit': 'matvec/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line, default=_json_default), flush=True)
 
@@ -250,6 +330,65 @@ def measure_fp64_peak(torch, dev, n=8192, reps=4):
     return 2.0 * n ** 3 / best / 1e9  # TFLOP/s
 
 
+def run_sweeps(torch, dist, A, para, steps, world, dev):
+    """time `steps` sweeps with CUDA events between barriers; returns dict of timings and counters (max over ranks)"""
+    from tnalg_b200.DMRG_anyH import sweep_once
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    mv0, fa0, fe0 = A.stats['n_matvec'], A.stats['flops_algorithmic'], A.stats['flops_executed']
+    A.timing = True
+    A.solver_time_ms(), A.phase_times_ms()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    torch.cuda.nvtx.range_push('timed')   # ncu --nvtx --nvtx-include "timed/" profiles exactly the timed sweeps
+    for _ in range(steps):
+        sweep_once(A, para)
+    torch.cuda.nvtx.range_pop()
+    e1.record()
+    barrier()
+    t_ms = max_over_ranks(e0.elapsed_time(e1))
+    solver_ms = max_over_ranks(A.solver_time_ms())
+    ph = A.phase_times_ms()
+    ph = {k: max_over_ranks(v) for k, v in ph.items()}
+    A.timing = False
+    return dict(t_ms=t_ms, solver_ms=solver_ms, gauge_ms=ph['gauge'], env_ms=ph['env'], n_mv=A.stats['n_matvec'] - mv0,
+                f_alg=A.stats['flops_algorithmic'] - fa0, f_exe=A.stats['flops_executed'] - fe0, barrier=barrier,
+                max_over_ranks=max_over_ranks)
+
+
+def quick_workload(torch, dist, name, world, dev, warmup=1, steps=1):
+    """a short run of another BASELINE configuration (sweep wall-time, matvecs/s) for the `other_workloads` block"""
+    from tnalg_b200.DMRG_anyH import sweep_once
+    from tnalg_b200.MPSClass import MpsOpenBoundaryClass
+    para = build_para(WORKLOADS[name])
+    np.random.seed(0)
+    A = MpsOpenBoundaryClass(para['l'], para['d'], para['chi'], operators=para['op'], is_save_op=True, eig_way=1)
+    A.sync_replicas()
+    A.correct_orthogonal_center(para['ob_position'])
+    for _ in range(warmup):
+        sweep_once(A, para)
+    r = run_sweeps(torch, dist, A, para, steps, world, dev)
+    out = {'L': para['l'], 'chi': para['chi'], 'ms_per_sweep': r['t_ms'] / steps, 'matvecs_per_s': r['n_mv'] / (r['t_ms'] * 1e-3),
+           'solver_ms_per_sweep': r['solver_ms'] / steps, 'gauge_qr_ms_per_sweep': r['gauge_ms'] / steps,
+           'env_update_ms_per_sweep': r['env_ms'] / steps, 'algorithmic_tflops_sweep': r['f_alg'] / (r['t_ms'] * 1e-3) / 1e12,
+           'warmup': warmup, 'steps': steps, 'n_gpus': world}
+    del A
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args, para, workload):
     import torch
     import torch.distributed as dist
@@ -264,24 +403,14 @@ def run_ours(args, para, workload):
     from tnalg_b200.DMRG_anyH import observe, sweep_once
     from tnalg_b200.MPSClass import MpsOpenBoundaryClass
     be = ops.backend()
+    if args.shard:
+        be.shard_mode = args.shard
     counts = site_counts(para)
     L, d, chi = para['l'], para['d'], para['chi']
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     np.random.seed(0)
     A = MpsOpenBoundaryClass(L, d, chi, operators=para['op'], is_save_op=True, eig_way=1)
+    A.sync_replicas()
     A.correct_orthogonal_center(para['ob_position'])
     for _ in range(args.warmup):
         sweep_once(A, para)
@@ -289,27 +418,18 @@ def run_ours(args, para, workload):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    mv0, fa0, fe0 = A.stats['n_matvec'], A.stats['flops_algorithmic'], A.stats['flops_executed']
     be.lib.tn_launch_count_reset()
-    A.timing = True
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    torch.cuda.nvtx.range_push('timed')   # ncu --nvtx --nvtx-include "timed/" profiles exactly the timed sweeps
-    for _ in range(args.steps):
-        sweep_once(A, para)
-    torch.cuda.nvtx.range_pop()
-    e1.record()
-    barrier()
-    t_ms = max_over_ranks(e0.elapsed_time(e1))
+    comm = be.comm()
+    coll0 = comm.collectives() if comm is not None else 0
+    r = run_sweeps(torch, dist, A, para, args.steps, world, dev)
+    barrier, max_over_ranks = r['barrier'], r['max_over_ranks']
+    t_ms, solver_ms, n_mv, f_alg, f_exe = r['t_ms'], r['solver_ms'], r['n_mv'], r['f_alg'], r['f_exe']
     launches = be.launch_count()
+    collectives = (comm.collectives() - coll0) if comm is not None else 0
     clocks = sampler.stop() if rank == 0 else None
-    solver_ms = max_over_ranks(A.solver_time_ms())
-    A.timing = False
-    n_mv = A.stats['n_matvec'] - mv0
-    f_alg = A.stats['flops_algorithmic'] - fa0
-    f_exe = A.stats['flops_executed'] - fe0
     value = n_mv / (t_ms * 1e-3)
+    sharding = A.last_eig.get('sharding', 'none')
+    not_conv = A.stats['not_converged']
 
     # ---- e2e: host buffers in, results out, through the drop-in API ----
     host = [t.cpu().pin_memory() for t in A.mps]
@@ -334,10 +454,12 @@ def run_ours(args, para, workload):
     widest = max(counts, key=lambda c: c['flop'])
     p = widest['site']
     A.correct_orthogonal_center(p)
+    a_w, b_w = A.mps[p].shape[0], A.mps[p].shape[2]
+    rows = be.shard_rows(a_w, d, b_w, rank, world) if world > 1 else None
     plan = A.effective_hamiltonian_plan(p, para['index1'], para['index2'], para['coeff1'], para['coeff2'], tol=para['eigs_tol'],
-                                        rank=rank if world > 1 else 0, world=world)
+                                        rank=rank if (world > 1 and rows is None) else 0, world=world if rows is None else 1, rows=rows)
     x = A.mps[p].clone()
-    y = torch.empty_like(x)
+    y = torch.empty_like(x) if rows is None else be.empty(rows[1], d, b_w)
     for _ in range(3):
         plan.matvec(x, 0.0, 1.0, out=y)
     torch.cuda.synchronize()
@@ -349,63 +471,100 @@ def run_ours(args, para, workload):
     r1.record()
     torch.cuda.synchronize()
     mv_ms = r0.elapsed_time(r1) / reps
-    achieved = plan.flops_algorithmic / world / (mv_ms * 1e-3) / 1e12 if world > 1 else plan.flops_algorithmic / (mv_ms * 1e-3) / 1e12
+    achieved = plan.flops_algorithmic / world / (mv_ms * 1e-3) / 1e12
     executed_tf = plan.flops_executed / (mv_ms * 1e-3) / 1e12
     executed_flop = plan.flops_executed
     uses_tma = plan.uses_tma
     plan.destroy()
+    # one QR gauge move at the widest matricisation (own Householder kernels)
+    Tq = A.mps[p]
+    for _ in range(2):
+        be.qr_tensor(Tq, True)
+    torch.cuda.synchronize()
+    r0.record()
+    for _ in range(4):
+        be.qr_tensor(Tq, True)
+    r1.record()
+    torch.cuda.synchronize()
+    qr_ms = r0.elapsed_time(r1) / 4
     peak = measure_fp64_peak(torch, dev)
-    traffic = None
+    dmma_peak = be.dmma_peak_tflops()
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
     if os.path.isfile(tpath):
         try:
-            traffic = json.load(open(tpath)).get(workload)
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj.get(workload), tj.get('source')
         except Exception:
             traffic = None
+
+    other = {}
+    if not args.no_other and workload == 'j1j2_6x6_chi1024':
+        del x, y
+        torch.cuda.empty_cache()
+        if world == 1:
+            for name in ('heis_chain100_chi256', 'xxz_chain200_chi512'):
+                other[name] = quick_workload(torch, dist, name, world, dev, warmup=1, steps=1)
+        elif world == 8 and args.with_cfg5:
+            A.clean_to_save()
+            del A
+            torch.cuda.empty_cache()
+            other['heis_8x8_chi2048'] = quick_workload(torch, dist, 'heis_8x8_chi2048', world, dev, warmup=1, steps=1)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    # ---- CPU baseline (rank 0, N = 1 only) ----
+    # ---- CPU baseline (rank 0, N = 1 only): one full local update of the oracle port at the widest cut ----
     cpu = None
     if world == 1 and not args.no_cpu:
-        s = cpu_matvec_sample(para, counts, budget_s=15.0, max_calls=3)
+        try:
+            from threadpoolctl import threadpool_limits
+            threadpool_limits(limits=os.cpu_count())
+        except Exception:
+            pass
+        s = cpu_local_update_sample(para, counts)
         per_site = default_matvecs_per_site(para, counts)
-        v, t = cpu_sweep_estimate(counts, s, per_site)
-        cpu = {'value': v, 'unit': 'matvec/s', 'cores': os.cpu_count(), 'kind': 'port',
-               'sample': ('%d calls of the reference matvec handle (oracle port, numpy BLAS) at the widest site a=b=%d K_L=%d '
-                          'K_R=%d n_x=%d (%.2f s each, %.1f GFLOP/s); sweep matvecs/s extrapolated by sum_p F_mv(p)'
-                          % (s['calls'], s['a'], s['kl'], s['kr'], s['nx'], s['t_widest'], s['flop_rate'] / 1e9)),
-               'sweep_s_extrapolated': t}
+        sweep_flop = sum(n * c['flop'] for n, c in zip(per_site, counts))
+        t = sweep_flop / s['mv_rate_flops']
+        cpu = {'value': sum(per_site) / t, 'unit': 'matvec/s', 'cores': blas_threads() or os.cpu_count(), 'kind': 'port',
+               'sample': ('ONE full local update of the reference path at the widest cut a=b=%d K_L=%d K_R=%d n_x=%d (oracle port: %d '
+                          'environment transfers %.2f s + scipy eigsh with %d handle calls %.2f s, %.0f GFLOP/s); sweep matvecs/s '
+                          'extrapolated by sum_p F_mv(p)' % (s['a'], s['kl'], s['kr'], s['nx'], s['n_transfers'], s['t_env'], s['calls'],
+                                                             s['t_eig'], s['flop_rate'] / 1e9)),
+               'sweep_s_extrapolated': t, 'host_cpus': os.cpu_count()}
+    other_ms = t_ms - solver_ms - r['gauge_ms'] - r['env_ms']
     line = {
         'metric': 'dmrg_sweep_matvecs_per_s', 'value': value, 'unit': 'matvec/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': t_ms / args.steps, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': workload, 'L': L, 'chi': chi, 'd': d, 'terms': int(para['index2'].shape[0]),
-                   'eigs_tol': para['eigs_tol'], 'ncv': A.lanczos_ncv, 'step': 'one full sweep = %d local updates' % (2 * L - 2),
-                   'l2': 'inputs larger than L2 (environment blocks of one matvec: %.0f MiB)'
-                         % ((widest['kl'] + widest['nx']) * widest['a'] ** 2 * 8 / 2 ** 20 + (widest['kr'] + widest['nx']) * widest['b'] ** 2 * 8 / 2 ** 20),
-                   'parallelism': 'terms sharded over %d GPU(s)' % world},
+        'config': config_block(para, workload, world, counts),
         'sweep': {'matvecs_per_sweep': n_mv / args.steps, 'solver_ms_per_sweep': solver_ms / args.steps,
                   'algorithmic_tflops_sweep': f_alg / (t_ms * 1e-3) / 1e12, 'algorithmic_tflops_solver': f_alg / (solver_ms * 1e-3) / 1e12,
-                  'executed_tflops_solver': f_exe / (solver_ms * 1e-3) / 1e12, 'not_converged': A.stats['not_converged']},
+                  'executed_tflops_solver_per_gpu': f_exe / (solver_ms * 1e-3) / 1e12, 'not_converged': not_conv,
+                  'sharding': sharding, 'collectives_per_sweep': collectives / args.steps,
+                  'phases_ms_per_sweep': {'solver (Lanczos: matvec + collectives + vector ops)': solver_ms / args.steps,
+                                          'gauge moves (Householder QR + absorb)': r['gauge_ms'] / args.steps,
+                                          'environment updates': r['env_ms'] / args.steps,
+                                          'plan build / merges / host gap': other_ms / args.steps}},
         'roofline': {'bound': 'tensor', 'kernel': 'chain_gemm_tma_kernel (left + right stage launches of one matvec at the widest site)',
                      'achieved': executed_tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': executed_tf / peak, 'traffic': traffic,
+                     'traffic_source': traffic_src,
                      'flop_per_matvec_executed': executed_flop, 'flop_per_matvec_reference_grouping': widest['flop'],
                      'achieved_reference_grouping': achieved, 'tma_stage_mask': uses_tma,
-                     'note': 'achieved = flop the two launches execute / CUDA-event time. Crossing terms that share an operator are summed '
+                     'note': 'achieved = flop the two launches execute (this rank) / CUDA-event time. Crossing terms that share an operator are summed '
                              'before the GEMM (same H_eff; e.g. n_x 42 -> 15 links at the widest 6x6 J1-J2 site), so the kernels execute fewer flop than the '
                              'reference grouping of SURVEY 8d (K_L, K_R, n_x); counted in reference-grouping flop the same matvec runs at '
-                             'achieved_reference_grouping TFLOP/s, which may exceed the hardware peak',
-                     'peak_source': 'cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry); '
-                                    'DMMA issue peak 37.09 TFLOP/s (profiles/r01_fp64_peaks.txt)',
+                             'achieved_reference_grouping TFLOP/s per GPU, which may exceed the hardware peak',
+                     'peak_source': 'cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)',
+                     'dmma_issue_peak_measured': dmma_peak, 'frac_of_dmma_issue_peak': executed_tf / dmma_peak,
                      'ms_per_matvec': mv_ms, 'site': p, 'a': widest['a'], 'b': widest['b'], 'K_L': widest['kl'], 'K_R': widest['kr'],
-                     'n_x': widest['nx']},
+                     'n_x': widest['nx'], 'rows_of_this_rank': None if rows is None else list(rows),
+                     'qr_ms_2chi_x_chi': qr_ms},
         'cpu_baseline': cpu,
         'e2e': {'value': e2e_value, 'unit': 'matvec/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': e2e_s * 1e3 / args.steps},
-        'gpu_launches': launches, 'clocks': clocks,
+        'gpu_launches': launches, 'clocks': clocks, 'other_workloads': other,
     }
     print(json.dumps(line, default=_json_default), flush=True)
     if world > 1:
@@ -422,7 +581,24 @@ def main():
     ap.add_argument('--chi', type=int, default=0, help='override the bond dimension (functional checks)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-e2e', action='store_true', help='skip the e2e leg (profiling runs)')
+    ap.add_argument('--no-other', action='store_true', help='skip the other_workloads block (chi=256 / chi=512 chains at N=1)')
+    ap.add_argument('--with-cfg5', action='store_true', help='N=8: add one sweep of the 8x8 chi=2048 workload to other_workloads')
+    ap.add_argument('--shard', default='', choices=['', 'rows', 'terms'], help="multi-GPU decomposition (default: 'rows')")
     args = ap.parse_args()
+    if args.impl == 'reference':
+        if int(os.environ.get('RANK', '0')) != 0:
+            return                                   # rank 0 alone runs the CPU arm
+        # torchrun exports OMP_NUM_THREADS=1; the CPU arm must use every host core: re-exec once with the BLAS pools opened up
+        n_cpu = str(os.cpu_count() or 1)
+        if os.environ.get('TNALG_BENCH_REEXEC') != '1' and any(os.environ.get(k) != n_cpu for k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS')):
+            env = dict(os.environ, OMP_NUM_THREADS=n_cpu, OPENBLAS_NUM_THREADS=n_cpu, MKL_NUM_THREADS=n_cpu, TNALG_BENCH_REEXEC='1')
+            sys.stdout.flush()
+            os.execve(sys.executable, [sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env)
+        try:
+            from threadpoolctl import threadpool_limits
+            threadpool_limits(limits=int(n_cpu))
+        except Exception:
+            pass
     para = build_para(WORKLOADS[args.workload], args.chi)
     workload = args.workload if not args.chi else '%s@chi%d' % (args.workload, args.chi)
     if args.impl == 'reference':

@@ -53,6 +53,9 @@ void tn_launch_count_reset(void);
 /* on != 0: bit-reproducible mode -- no stream-K split, no FP64-atomic combination of partial tiles, no concurrent matvec
  * stages (every output tile is summed by one CTA in a fixed order).  Returns the previous setting.  Default off. */
 int tn_set_deterministic(int on);
+/* issue-rate ceiling of the FP64 tensor pipe (DMMA.8x8x4 from registers on every SM), TFLOP/s, measured now on the current
+ * device; scratch: [dev] 8 * 512 * sm_count bytes.  Blocking (a few ms). */
+int tn_measure_dmma_peak(double* tflops_out /* [host] */, void* scratch /* [dev] */, size_t scratch_bytes, void* stream);
 
 /* --------------------------------------------------------------------------------------------------
  * Chain GEMM: the FP64 tensor-core (DMMA) contraction engine every tensor-network contraction below is built

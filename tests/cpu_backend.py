@@ -284,14 +284,13 @@ class CpuBackend:
             matvec(e, y)
             H[:, j] = y.numpy()
         H = 0.5 * (H + H.T)
+        basis = np.eye(n)
         if locked is not None and locked.shape[0]:
-            Lk = locked.numpy()
-            P = np.eye(n) - Lk.T @ Lk
-            H = P @ H @ P
-            H += 1e6 * (np.sign(tau) or 1.0) * Lk.T @ Lk   # push the deflated directions to the other end of the spectrum
-        w, v = np.linalg.eigh(H)
+            q, _ = np.linalg.qr(locked.numpy().T, mode='complete')
+            basis = q[:, locked.shape[0]:]                 # orthogonal complement of the locked vectors
+        w, v = np.linalg.eigh(basis.T @ H @ basis)
         best = int(np.argmax(np.abs(1.0 - tau * w)))
-        return 1.0 - tau * w[best], torch.from_numpy(np.ascontiguousarray(v[:, best])), n, 0.0, True
+        return 1.0 - tau * w[best], torch.from_numpy(np.ascontiguousarray(basis @ v[:, best])), n, 0.0, True
 
     def scale_diag_rows(self, S, Vt):
         return S[:, None] * Vt

@@ -58,7 +58,8 @@ def test_observables_on_reference_snapshot(golden):
         assert np.abs(A.observe_magnetization(3) - g['ob_mz']).max() < 1e-11
 
 
-@pytest.mark.parametrize('case', ['e2e_chain12', 'e2e_xxz10', 'e2e_j1j2_4x2', 'e2e_spin1_chain8'])
+@pytest.mark.parametrize('case', ['e2e_chain12', 'e2e_xxz10', 'e2e_j1j2_4x2', 'e2e_spin1_chain8', 'e2e_longrange8', 'e2e_square3x2',
+                                  'e2e_periodic8'])
 def test_end_to_end_vs_reference(golden, case):
     """converged, tight-tolerance runs: sweep energies and truncated spectrum rel 1e-10, observables abs 1e-8"""
     from tnalg_b200.DMRG_anyH import dmrg_finite_size
@@ -76,6 +77,18 @@ def test_end_to_end_vs_reference(golden, case):
     assert np.array_equal(A.virtual_dim, g['virtual_dim'])
     assert info['not_converged'] == 0
     assert all(isinstance(t, np.ndarray) for t in A.mps)
+
+
+@pytest.mark.parametrize('case', ['e2e_full6', 'e2e_jigsaw7'])
+def test_energy_parity_on_degenerate_lattices(golden, case):
+    """all-to-all and spin-1 jigsaw lattices have degenerate ground multiplets: only the energy is a parity quantity"""
+    from tnalg_b200.DMRG_anyH import dmrg_finite_size
+    g = golden(case)
+    para = para_from_golden(g)
+    np.random.seed(int(g['seed']))
+    ob, A, info, para = dmrg_finite_size(para)
+    assert abs(ob['e_per_site'][0] - g['e_per_site'][0]) <= 1e-10 * abs(g['e_per_site'][0])
+    assert info['not_converged'] == 0
 
 
 def test_size_independent_properties_chi64():
@@ -187,13 +200,75 @@ def _full_size_checks(chi, n_ranks):
     assert e_after <= e_obs + 1e-9 * abs(e_obs)
     assert A.last_eig['converged'] and abs((1.0 - A.last_eig['lambda']) / para['tau'] - e_after) < 1e-6 * abs(e_after)
     plan.destroy()
+    return A, para, p
+
+
+def _oracle_handle_from_blocks(A, para, p, x):
+    """the reference handle (oracle.apply_handle, MPSClass.py:755-776) evaluated on the host with the UNMERGED opt_env groups
+    ('1_0_1' as the literal list of crossing terms) copied from the device blocks"""
+    from oracle import dmrg_oracle as orc
+    from tnalg_b200 import ops
+    be = ops.backend()
+    env = A._environments(para['index1'], para['index2'], para['coeff1'], para['coeff2'], para['eigs_tol'])
+    env.ensure(p, A.mps)
+    a, d, b = A.mps[p].shape
+    env.merge_crossing = False
+    try:
+        g = env.groups(p, d)
+    finally:
+        env.merge_crossing = True
+    h = lambda t: be.to_numpy(t)  # noqa: E731
+    site_ops = [np.eye(d)] + [np.asarray(o) for o in g['ls_ops']] + [np.asarray(o) for o in g['rs_ops']]   # index 0 is reserved ('1_0_0')
+    oenv = {}
+    if g['HL'] is not None:
+        oenv['1_0_0'] = h(g['HL'])
+    if g['HR'] is not None:
+        oenv['0_0_1'] = h(g['HR'])
+    if g['M'] is not None:
+        oenv['0_99_0'] = np.asarray(g['M'])
+    for k, m in enumerate(g['LS']):
+        oenv['1_%d_0' % (k + 1)] = h(m)
+    for k, m in enumerate(g['RS']):
+        oenv['0_%d_1' % (len(g['LS']) + k + 1)] = h(m)
+    if g['XL']:
+        oenv['1_0_1'] = [[c, h(l), h(r)] for c, l, r in zip(g['x_coeff'], g['XL'], g['XR'])]
+    O = orc.OracleMps(2, d, 2, site_ops, mps=[np.zeros((1, d, 2)), np.zeros((2, d, 1))])
+    return O.apply_handle(x.reshape(-1), oenv, (a, d, b), para['tau']), len(g['XL'])
 
 
 def test_full_size_properties_chi1024():
-    """BASELINE.json's full size (6x6 J1-J2, chi = 1024, a = b = 1024 at the probed site): far beyond what the oracle can run,
-    so parity is anchored on properties: symmetry, linearity, shard additivity, the energy of the state computed by the
-    matvec path against the same energy from the observable path, and a variational local update"""
-    _full_size_checks(1024, 4)
+    """BASELINE.json's full size (6x6 J1-J2, chi = 1024, a = b = 1024, K_L = K_R = 4, n_x = 42 at the probed site 11):
+    (i) size-independent properties -- symmetry, linearity, shard additivity, the energy of the state computed by the matvec
+    path against the same energy from the observable path, a variational local update;
+    (ii) DIRECT parity at the metric shape: the merged 15-link CUDA plan against the reference handle evaluated by the oracle
+    on the unmerged 42 crossing terms (1e-13 relative), and one left-to-right and one right-to-left environment update
+    against oracle.transfer_l2r / transfer_r2l at chi = 1024"""
+    from oracle import dmrg_oracle as orc
+    from tnalg_b200 import ops
+    be = ops.backend()
+    A, para, p = _full_size_checks(1024, 4)
+    shape = tuple(A.mps[p].shape)
+    assert shape == (1024, 2, 1024)
+    rng = np.random.RandomState(5)
+    x = rng.randn(*shape)
+    plan = A.effective_hamiltonian_plan(p, para['index1'], para['index2'], para['coeff1'], para['coeff2'], tol=para['eigs_tol'])
+    got = be.to_numpy(plan.matvec(be.from_numpy(x), 1.0, -para['tau'])).reshape(-1)
+    hx = be.to_numpy(plan.matvec(be.from_numpy(x), 0.0, 1.0)).reshape(-1)
+    plan.destroy()
+    ref, n_cross = _oracle_handle_from_blocks(A, para, p, x)
+    assert n_cross == 42
+    assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max()
+    href = (x.reshape(-1) - ref) / para['tau']          # H x from the reference handle (loses ~4 digits to the shift)
+    assert np.abs(hx - href).max() <= 1e-9 * np.abs(href).max()
+    # environment updates at chi = 1024 (a5)
+    T = A.mps[p]
+    Tn = be.to_numpy(T)
+    E = rng.randn(1024, 1024)
+    op = np.array([[0.3, -1.2], [0.7, 0.4]])
+    for direction, fn in ((0, orc.transfer_l2r), (1, orc.transfer_r2l)):
+        out = be.to_numpy(be.env_update(direction, T, [[(be.from_numpy(E), op)]])[0])
+        want = fn(Tn, op, E)
+        assert np.abs(out - want).max() <= 1e-13 * np.abs(want).max(), direction
 
 
 def test_rdm_full_state_dense_heff_and_checks(golden):

@@ -510,3 +510,75 @@ def test_lattice_generators_match_reference_tables(golden):
         for k in ('coeff1', 'coeff2'):
             assert np.allclose(np.asarray(para[k], dtype=float).reshape(-1), g[k].reshape(-1), rtol=0, atol=1e-15), (name, k)
         assert len(para['op']) == g['op'].shape[0] and all(np.allclose(a, b) for a, b in zip(para['op'], g['op'])), name
+
+
+def test_environment_cache_is_keyed_on_content(cpu_be):
+    """an in-place edit of para['coeff2'] must not leave stale environments (the reference rebuilds them
+    from coeff* on every update_tensor_eigs call, MPSClass.py:633-682) -- the reproduction of the advisor, on the stand-in"""
+    from oracle import dmrg_oracle as orc
+    from tnalg_b200 import Parameters as Pm
+    from tnalg_b200.DMRG_anyH import observe, sweep_once
+    from tnalg_b200.MPSClass import MpsOpenBoundaryClass
+    para = Pm.generate_parameters_dmrg('chain')
+    para.update(l=6, chi=8, eigs_tol=1e-12)
+    para = Pm.make_consistent_parameter_dmrg(para)
+    np.random.seed(0)
+    A = MpsOpenBoundaryClass(para['l'], para['d'], para['chi'], operators=para['op'], is_save_op=True, eig_way=1)
+    A.correct_orthogonal_center(0)
+    for _ in range(3):
+        sweep_once(A, para)
+    env_before = A._env
+    sweep_once(A, para)
+    assert A._env is env_before                     # unchanged couplings: the cache is reused
+    para['coeff2'][2::3] *= 3.0
+    for _ in range(6):
+        sweep_once(A, para)
+    assert A._env is not env_before
+    e = observe(A, para, {})['e_per_site'][0] * para['l']
+    e_ed = np.linalg.eigvalsh(orc.dense_hamiltonian(para))[0]
+    assert abs(e - e_ed) < 1e-9 * abs(e_ed)
+    # an operator edited in place (the field term op[6] after hx changes) is seen as well
+    env_before = A._env
+    para['op'][6][:] = -0.4 * np.real(para['op'][1])
+    sweep_once(A, para)
+    assert A._env is not env_before
+
+
+def test_eig_way_0_and_complex_operator_errors(cpu_be):
+    from oracle import dmrg_oracle as orc
+    from tnalg_b200 import Parameters as Pm
+    from tnalg_b200.DMRG_anyH import dmrg_finite_size
+    from tnalg_b200.MPSClass import MpsOpenBoundaryClass
+    para = Pm.generate_parameters_dmrg('chain')
+    para.update(l=6, chi=8, eigs_tol=1e-12, break_tol=1e-13, eigWay=0, dt_ob=1)
+    para = Pm.make_consistent_parameter_dmrg(para)
+    np.random.seed(0)
+    ob, A, info, _ = dmrg_finite_size(para)
+    e_ed = np.linalg.eigvalsh(orc.dense_hamiltonian(para))[0]
+    assert abs(ob['e_per_site'][0] * para['l'] - e_ed) < 1e-9 * abs(e_ed)
+    np.random.seed(0)
+    B = MpsOpenBoundaryClass(4, 2, 4)
+    B.correct_orthogonal_center(1)
+    with pytest.raises(ValueError, match='complex'):
+        B.observe_magnetization(2)
+    B.eig_way = 0
+    B.mps[1] = np.random.randn(4, 2, 4)
+    with pytest.raises(ValueError, match='eig_way=0'):
+        B._dense_solve(None, (64, 2, 64), None, 1e-4)
+
+
+def test_eigs_fh_host_logic(cpu_be):
+    """a8' call shape on the stand-in: callable lin_map, n > 1 by deflation, which = sa / la / lm"""
+    from tnalg_b200.Eigs_Module_sjr import eigs_fh
+    rng = np.random.RandomState(0)
+    d = 24
+    g = rng.randn(d, d)
+    H = (g + g.T) / 2
+    w, V = np.linalg.eigh(H)
+    lm, v, info = eigs_fh(lambda x: H @ x.numpy(), d, n=3, which='sa', tol=1e-12)
+    assert lm.shape == (3,) and v.shape == (d, 3) and np.abs(lm - w[:3]).max() < 1e-8
+    lm, v, info = eigs_fh(lambda x: H @ x.numpy(), d, n=2, which='la')
+    assert np.abs(lm - w[::-1][:2]).max() < 1e-8
+    lm, v, info = eigs_fh(lambda x: H @ x.numpy(), d, n=1, which='lm')
+    assert abs(abs(lm[0]) - np.abs(w).max()) < 1e-7
+    assert set(info) >= {'it_time', 'error'}

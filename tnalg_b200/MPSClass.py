@@ -120,8 +120,9 @@ class MpsOpenBoundaryClass(MpsBasic):
                       't_solve': 0.0, 'not_converged': 0}
         self.lanczos_ncv = 20           # ARPACK's default ncv for k=1 (scipy eigsh)
         self.lanczos_max_restarts = 2000
-        self.timing = False             # when True, update_tensor_eigs records solver time with CUDA events
-        self._events = []
+        self.timing = False             # when True, update_tensor_eigs records per-phase times with CUDA events
+        self._events = []               # solver (Lanczos) intervals
+        self._phase_events = {'gauge': [], 'env': []}
 
     def _ensure_device(self):
         if not hasattr(self, '_be') or self._be is None:
@@ -390,13 +391,35 @@ class MpsOpenBoundaryClass(MpsBasic):
             vec = -vec
         return float(w_host[best]), vec, n, 0.0, True
 
+    def _phase(self, name):
+        """context manager: CUDA-event interval of one phase of a local update (only while self.timing)"""
+        import contextlib
+        import torch
+
+        @contextlib.contextmanager
+        def cm():
+            if not self.timing:
+                yield
+                return
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            try:
+                yield
+            finally:
+                e1.record()
+                self._phase_events[name].append((e0, e1))
+        return cm()
+
     def update_tensor_eigs(self, p, index1, index2, coeff1, coeff2, tau, is_real, tol=1e-16):
         self._ensure_device()
         if self.center < -0.5:
             raise RuntimeError('CenterError: central-orthogonalize MPS before updating the tensor')
-        self.correct_orthogonal_center(p)
+        with self._phase('gauge'):
+            self.correct_orthogonal_center(p)
         env = self._environments(index1, index2, coeff1, coeff2, tol)
         shape = tuple(self.mps[p].shape)
+        with self._phase('env'):
+            env.ensure(p, self.mps)
         vec = self._solve(lambda rank, world, rows: env.plan(p, self.mps, rank=rank, world=world, rows=rows), shape,
                           self.mps[p], tau, tol)
         self.mps[p] = vec.reshape(shape)
@@ -452,6 +475,15 @@ class MpsOpenBoundaryClass(MpsBasic):
         t = sum(e0.elapsed_time(e1) for e0, e1 in self._events)
         self._events = []
         return t
+
+    def phase_times_ms(self):
+        """{'gauge': ms, 'env': ms} of the intervals recorded while self.timing was True (gauge = QR centre moves,
+        env = environment updates of the bond moves)"""
+        import torch
+        torch.cuda.synchronize()
+        out = {k: sum(e0.elapsed_time(e1) for e0, e1 in v) for k, v in self._phase_events.items()}
+        self._phase_events = {k: [] for k in self._phase_events}
+        return out
 
     # ---- a11: entanglement (MPSClass.py:812-839) ----
     def calculate_entanglement_spectrum(self, if_fast=True):

@@ -38,6 +38,7 @@ SIGNATURES = {
     'tn_launch_count': (C.c_longlong, []),
     'tn_launch_count_reset': (None, []),
     'tn_set_deterministic': (C.c_int, [C.c_int]),
+    'tn_measure_dmma_peak': (C.c_int, [c_double_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'tn_chain_gemm_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),
     'tn_chain_gemm': (C.c_int, [C.c_int] * 8 + [C.POINTER(TnProblem), C.c_int, C.POINTER(TnLink), C.c_int, C.c_int,
                                               C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -173,6 +173,13 @@ class CudaBackend:
         self._comm = Comm(self, handle, rank, world)
         return self._comm
 
+    def dmma_peak_tflops(self):
+        """issue-rate ceiling of the FP64 tensor pipe measured on this device (tn_measure_dmma_peak)"""
+        ws = self.workspace('peak', 8 * 512 * self.sm_count)
+        out = C.c_double()
+        L.check(self.lib.tn_measure_dmma_peak(C.byref(out), _ptr(ws), ws.numel(), self.stream()))
+        return out.value
+
     def set_deterministic(self, on=True):
         """bit-reproducible kernels (no stream-K split, no FP64-atomic tile combination, no concurrent matvec stages)"""
         return bool(self.lib.tn_set_deterministic(1 if on else 0))
@@ -508,7 +515,13 @@ class CudaBackend:
         return S[:, None] * Vt
 
     def norm(self, x):
-        return float(torch.linalg.vector_norm(x))
+        """2-norm through the deterministic dot kernel (tn_dot); blocking"""
+        x = x.contiguous().reshape(-1)
+        if not hasattr(self, '_norm_slot'):
+            self._norm_slot = torch.zeros(1, dtype=torch.float64, device=self.device)
+        ws = self.workspace('dot', self.lib.tn_dot_workspace_bytes(x.numel()))
+        L.check(self.lib.tn_dot(_ptr(x), _ptr(x), x.numel(), _ptr(self._norm_slot), _ptr(ws), ws.numel(), self.stream()))
+        return float(self._norm_slot.item()) ** 0.5
 
 
 def _alias(ptr, count, device):
