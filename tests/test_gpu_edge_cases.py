@@ -32,11 +32,7 @@ def test_edge_case_energy(name, kw, exact, two_site):
     from tnalg_b200 import DMRG_anyH
     para = _para(kw)
     np.random.seed(0)
-    if two_site and para['d'] ** 2 > 4:
-        with pytest.raises(NotImplementedError):     # d*d = 9 > TN_MAX_PHYS_DIM: refused loudly, no fallback
-            DMRG_anyH.dmrg_finite_size_two_site(para, chi_init=2)
-        return
-    if two_site:
+    if two_site:     # d*d = 9 (spin-1) runs too: site operators beyond TN_MAX_LOADPATH_DIM are pre-applied element-wise
         ob, A, info, _ = DMRG_anyH.dmrg_finite_size_two_site(para, chi_init=min(2, para['chi']))
     else:
         ob, A, info, _ = DMRG_anyH.dmrg_finite_size(para)
