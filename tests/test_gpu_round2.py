@@ -129,14 +129,20 @@ def test_eig_way_0_solves_the_dense_matrix(be, golden):
     from tests.test_gpu_dmrg import para_from_golden
     from tnalg_b200.DMRG_anyH import dmrg_finite_size
     g = golden('e2e_chain12')
-    para = para_from_golden(g, eigWay=0, chi=8, l=8)
-    para2 = para_from_golden(g, eigWay=1, chi=8, l=8)
+    from tnalg_b200 import Parameters as Pm
+
+    def make(way):
+        para = Pm.generate_parameters_dmrg('chain')
+        para.update(l=8, chi=16, eigs_tol=1e-12, break_tol=1e-13, dt_ob=1, eigWay=way)
+        return Pm.make_consistent_parameter_dmrg(para)
+    para, para2 = make(0), make(1)
+    assert g['e_per_site'].size == 1
     np.random.seed(3)
     ob0, A0, info0, _ = dmrg_finite_size(para)
     np.random.seed(3)
     ob1, A1, info1, _ = dmrg_finite_size(para2)
     e_ed = np.linalg.eigvalsh(orc.dense_hamiltonian(para))[0] / para['l']
-    assert abs(ob0['e_per_site'][0] - ob1['e_per_site'][0]) < 1e-10 and abs(ob0['e_per_site'][0] - e_ed) < 1e-8
+    assert abs(ob0['e_per_site'][0] - ob1['e_per_site'][0]) < 1e-10 and abs(ob0['e_per_site'][0] - e_ed) < 1e-10
     assert info0['n_matvec'] > info1['n_matvec']       # the dense path applies the plan to every unit vector
 
 
@@ -145,8 +151,7 @@ def test_exact_diagonalisation_on_device_vs_dense(be):
     from tnalg_b200.EDspinClass import EDbasic
     para = orc.make_para('chain', l=10, chi=8, jxy=1.0, jz=0.5, hx=0.0, hz=0.0)
     H = orc.dense_hamiltonian(para)
-    ops_ = orc.spin_operators('half')
-    sx, sy, sz = ops_['sx'], ops_['sy'], ops_['sz']
+    _, sx, sy, sz, _, _ = orc.spin_operators('half')
     h2 = np.real(1.0 * (np.kron(sx, sx) + np.kron(sy, sy)) + 0.5 * np.kron(sz, sz))
     L = 10
     couplings = np.array([[i, i + 1, 0] for i in range(L - 1)])
@@ -239,8 +244,7 @@ def test_observables_chi512_vs_oracle(be):
     MPS with chi = 512 (L = 22: bonds 1,2,...,512,...,2,1) against the oracle's transfer chains, abs 1e-8 (measured ~1e-13)"""
     from tnalg_b200.MPSClass import MpsOpenBoundaryClass
     L, d, chi = 22, 2, 512
-    ops_ = orc.spin_operators('half')
-    oplist = [np.real(ops_[k]) if np.abs(np.imag(ops_[k])).max() == 0 else ops_[k] for k in ('id', 'sx', 'sy', 'sz', 'su', 'sd')]
+    oplist = [np.real(o) if np.abs(np.imag(o)).max() == 0 else o for o in orc.spin_operators('half')]
     np.random.seed(11)
     A = MpsOpenBoundaryClass(L, d, chi, operators=oplist)
     A.correct_orthogonal_center(L // 2)

@@ -29,12 +29,15 @@ namespace tn {
 
 namespace {
 constexpr int QNB = 32;        // panel width
-constexpr int QTHREADS = 512;  // 16 warps
+constexpr int QTHREADS = 512;  // panel kernel: 16 warps
 constexpr int QWARPS = QTHREADS / 32;
 constexpr int QMAXC = 8;       // portable cluster size
 constexpr int QSLOT = 2 * QNB; // doubles one CTA contributes per column: g[32], row j[32]
-constexpr int QMAX_ROWS_PER_CTA = 768;
+constexpr int QMAX_RPT = 48;   // rows per thread of the panel kernel -> 768 rows per CTA, 6144 per cluster
 constexpr int QNC = 16;        // strip width of the apply kernel
+constexpr int ATHREADS = 256;  // apply kernel: 8 warps
+constexpr int AWARPS = ATHREADS / 32;
+constexpr int AVP = QNB + 4;   // pitch of the reflector block in shared memory (conflict-free fragment reads)
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
@@ -45,78 +48,91 @@ __device__ __forceinline__ double warp_sum_q(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-
-size_t panel_smem_bytes(int R) {
-  return sizeof(double) * ((size_t)R * QNB + QWARPS * QNB + 2 * QMAXC * QSLOT + 2 * QNB * QNB + QNB);
-}
 }  // namespace
 
-// W: work matrix (m x n, leading dimension ld); panel = columns [j0, j0 + nbp), rows [j0, m)
+// W: work matrix (m x n, leading dimension ld); panel = columns [j0, j0 + nbp), rows [j0, m).
+// Register-resident panel: thread (warp w, lane k) holds column k of the rows  row_lo + i*16 + w  (i < RPT) of this CTA, so the
+// column-j broadcast is a warp shuffle and the rank-1 update touches registers only; shared memory carries just the
+// cross-warp / cross-CTA partial sums (double-buffered by the parity of j: ONE CTA barrier -- plus one cluster barrier when
+// the panel spans several CTAs -- per column).
+template <int RPT>
 __global__ void __launch_bounds__(QTHREADS, 1) qr_panel_kernel(double* __restrict__ W, int ld, int m, int j0, int nbp,
-                                                               double* __restrict__ tau_out, double* __restrict__ T_out, int R) {
+                                                               double* __restrict__ tau_out, double* __restrict__ T_out) {
   cg::cluster_group cluster = cg::this_cluster();
   const int C = (int)cluster.num_blocks(), c = (int)cluster.block_rank();
-  extern __shared__ __align__(16) double sm[];
-  double* P = sm;                          // R x 32, this CTA's rows of the panel
-  double* red = P + (size_t)R * QNB;       // 16 x 32 cross-warp partial sums
-  double* slots = red + QWARPS * QNB;      // [parity][source CTA][64]
-  double* Z = slots + 2 * QMAXC * QSLOT;   // Z[k*32 + j] = V_k^T v_j (k < j)
-  double* Ts = Z + QNB * QNB;              // compact-WY factor
-  double* taus = Ts + QNB * QNB;
+  __shared__ double red[2][QWARPS][QNB];        // per-warp partial Gram rows
+  __shared__ double rowj[2][QNB];               // row j of the panel (CTA 0)
+  __shared__ double slots[2][QMAXC][QSLOT];     // cluster exchange: [parity][source CTA][g(32) | row j(32)]
+  __shared__ double Z[QNB * QNB];               // Z[k*32 + j] = V_k^T v_j (k < j)
+  __shared__ double Ts[QNB * QNB];              // compact-WY factor
+  __shared__ double taus[QNB];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rows_total = m - j0;
-  const int row_lo = c * R;
-  const int nloc = max(0, min(R, rows_total - row_lo));
+  const int row_lo = c * (RPT * QWARPS);        // first panel row of this CTA
 
-  for (int idx = tid; idx < nloc * QNB; idx += QTHREADS) {
-    const int r = idx >> 5, k = idx & 31;
-    P[idx] = k < nbp ? W[(size_t)(j0 + row_lo + r) * ld + j0 + k] : 0.0;
+  double x[RPT];
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    const int pr = row_lo + i * QWARPS + warp;  // panel row
+    x[i] = (pr < rows_total && lane < nbp) ? W[(size_t)(j0 + pr) * ld + j0 + lane] : 0.0;
   }
-  for (int idx = tid; idx < 2 * QNB * QNB + QNB; idx += QTHREADS) Z[idx] = 0.0;  // Z, Ts, taus are contiguous
+  for (int idx = tid; idx < QNB * QNB; idx += QTHREADS) {
+    Z[idx] = 0.0;
+    Ts[idx] = 0.0;
+  }
+  if (tid < QNB) taus[tid] = 0.0;
   __syncthreads();
   if (C > 1) cluster.sync();  // every CTA of the cluster is resident before remote shared memory is written
 
   for (int j = 0; j < nbp; ++j) {
-    // ---- row j of the panel Gram matrix over this CTA's rows with panel index >= j ----
-    const int r_begin = max(0, j - row_lo);
+    const int par = j & 1;
+    // ---- row j of the panel Gram matrix, g_k = sum_{rows >= j} P[r,j] P[r,k], over this thread's rows ----
     {
-      double acc = 0.0, acc1 = 0.0;
-      int r = r_begin + warp;
-      for (; r + QWARPS < nloc; r += 2 * QWARPS) {
-        acc += P[r * QNB + j] * P[r * QNB + lane];
-        acc1 += P[(r + QWARPS) * QNB + j] * P[(r + QWARPS) * QNB + lane];
+      double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const double xj = __shfl_sync(0xffffffffu, x[i], j);
+        const double pr = (row_lo + i * QWARPS + warp >= j) ? xj * x[i] : 0.0;
+        if (i & 1) acc1 += pr; else acc0 += pr;
       }
-      if (r < nloc) acc += P[r * QNB + j] * P[r * QNB + lane];
-      red[warp * QNB + lane] = acc + acc1;
+      red[par][warp][lane] = acc0 + acc1;
+      if (c == 0 && warp == (j & (QWARPS - 1))) rowj[par][lane] = (RPT > 1 && j >= QWARPS) ? x[RPT > 1 ? 1 : 0] : x[0];  // row j = i*16 + warp
     }
     __syncthreads();
-    const int par = (j & 1) * QMAXC * QSLOT;
-    if (warp == 0) {
-      double g = 0.0;
+    double gk = 0.0, gj = 0.0, rjk, alpha;
+    if (C == 1) {
 #pragma unroll
-      for (int w = 0; w < QWARPS; ++w) g += red[w * QNB + lane];
-      const double rj = (c == 0) ? P[j * QNB + lane] : 0.0;  // the diagonal block lives in CTA 0 (R >= 32 when C > 1)
-      if (C == 1) {
-        slots[par + lane] = g;
-        slots[par + QNB + lane] = rj;
-      } else {
+      for (int w = 0; w < QWARPS; ++w) {
+        gk += red[par][w][lane];
+        gj += red[par][w][j];
+      }
+      rjk = rowj[par][lane];
+      alpha = rowj[par][j];
+    } else {
+      if (warp == 0) {
+        double g = 0.0;
+#pragma unroll
+        for (int w = 0; w < QWARPS; ++w) g += red[par][w][lane];
+        const double rj = (c == 0) ? rowj[par][lane] : 0.0;
         for (int dst = 0; dst < C; ++dst) {
-          double* remote = cluster.map_shared_rank(slots, dst);
-          remote[par + c * QSLOT + lane] = g;
-          remote[par + c * QSLOT + QNB + lane] = rj;
+          double* remote = cluster.map_shared_rank(&slots[0][0][0], dst);
+          remote[(par * QMAXC + c) * QSLOT + lane] = g;
+          remote[(par * QMAXC + c) * QSLOT + QNB + lane] = rj;
         }
       }
+      cluster.sync();
+      for (int s = 0; s < C; ++s) {
+        gk += slots[par][s][lane];
+        gj += slots[par][s][j];
+      }
+      rjk = slots[par][0][QNB + lane];
+      alpha = slots[par][0][QNB + j];
     }
-    if (C > 1) cluster.sync(); else __syncthreads();
-    // ---- every thread: the reduced row (its own column `lane`) and the scalars of column j ----
-    double gk = 0.0, gj = 0.0;
-    for (int s = 0; s < C; ++s) {
-      gk += slots[par + s * QSLOT + lane];
-      gj += slots[par + s * QSLOT + j];
-    }
-    const double rjk = slots[par + QNB + lane], alpha = slots[par + QNB + j];
     double tau, beta, scale;
-    if (rows_total - 1 - j == 0 || gj == 0.0) {  // nothing below the diagonal, or a zero column: H = 1 (dlarfg)
+    // nothing below the diagonal, or a column that is zero to the underflow threshold (its sum of squares would be formed from
+    // denormal products: exactly dependent columns shrink by 1e-16 per reflector under FMA and get there): H = 1, as dlarfg
+    // does for a zero tail; the sub-diagonal entries are cleared (scale = 0), a perturbation of 1e-140 of the input
+    if (rows_total - 1 - j == 0 || !(gj > 1e-280)) {
       tau = 0.0; beta = alpha; scale = 0.0;
     } else {
       const double nrm = sqrt(gj);
@@ -126,22 +142,26 @@ __global__ void __launch_bounds__(QTHREADS, 1) qr_panel_kernel(double* __restric
     }
     const double y = (gk - beta * rjk) * scale;  // k > j: v^T a_k;  k < j: V_k^T v_j
     const double ty = tau * y;
-    // ---- apply H_j to the columns k > j of this CTA's rows, store v below the diagonal ----
-    const int r_start = max(0, j + 1 - row_lo);
-    for (int r = r_start + warp; r < nloc; r += QWARPS) {
-      const double vr = P[r * QNB + j] * scale;
-      __syncwarp();
-      if (lane > j) P[r * QNB + lane] -= ty * vr;
-      else if (lane == j) P[r * QNB + j] = vr;
+    // ---- apply H_j to the columns k > j (registers only), store v below the diagonal and beta on it ----
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const double xj = __shfl_sync(0xffffffffu, x[i], j);
+      const int pr = row_lo + i * QWARPS + warp;
+      if (pr > j) {
+        const double vr = xj * scale;
+        if (lane > j) x[i] -= ty * vr;
+        else if (lane == j) x[i] = vr;
+      } else if (pr == j) {
+        if (lane > j) x[i] -= ty;
+        else if (lane == j) x[i] = beta;
+      }
     }
-    if (c == 0 && warp == (j & (QWARPS - 1))) {  // row j itself (v_j = 1); the warp that owns no other role this column
-      if (lane > j) P[j * QNB + lane] -= ty;
-      else if (lane == j) P[j * QNB + j] = beta;
-      else Z[lane * QNB + j] = y;
+    if (c == 0 && warp == (j & (QWARPS - 1))) {  // the warp that owns row j records the T-factor inputs
+      if (lane < j) Z[lane * QNB + j] = y;
       if (lane == j) taus[j] = tau;
     }
-    __syncthreads();
   }
+  __syncthreads();
 
   // ---- compact-WY factor: T[j,j] = tau_j, T[0:j, j] = -tau_j T[0:j,0:j] Z[0:j, j]  (dlarft, forward columnwise) ----
   if (c == 0) {
@@ -158,53 +178,61 @@ __global__ void __launch_bounds__(QTHREADS, 1) qr_panel_kernel(double* __restric
     for (int idx = tid; idx < QNB * QNB; idx += QTHREADS) T_out[idx] = Ts[idx];
     if (tid < nbp) tau_out[j0 + tid] = taus[tid];
   }
-  for (int idx = tid; idx < nloc * QNB; idx += QTHREADS) {
-    const int r = idx >> 5, k = idx & 31;
-    if (k < nbp) W[(size_t)(j0 + row_lo + r) * ld + j0 + k] = P[idx];
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    const int pr = row_lo + i * QWARPS + warp;
+    if (pr < rows_total && lane < nbp) W[(size_t)(j0 + pr) * ld + j0 + lane] = x[i];
   }
   if (C > 1) cluster.sync();  // no CTA exits while a peer may still address its shared memory
 }
 
-// unit-lower-trapezoidal reflector block stored below the diagonal of the panel columns of Wv
-__device__ __forceinline__ double qr_vload(const double* __restrict__ Wv, int ldv, int m, int j0, int nbp, int r, int k) {
-  if (r >= m || k >= nbp) return 0.0;
-  const int rl = r - j0;
-  if (rl < k) return 0.0;
-  if (rl == k) return 1.0;
-  return Wv[(size_t)r * ldv + j0 + k];
-}
-
-// Cm[j0:m, c_begin:c_end] <- (1 - V op(T) V^T) Cm[j0:m, c_begin:c_end];  transT != 0: op(T) = T^T
-__global__ void __launch_bounds__(QTHREADS, 1) qr_apply_kernel(const double* __restrict__ Wv, int ldv, int m, int j0, int nbp,
+// Cm[j0:m, c_begin:c_end] <- (1 - V op(T) V^T) Cm[j0:m, c_begin:c_end];  transT != 0: op(T) = T^T.
+// One cluster per strip of 16 columns; the CTAs of the cluster split the rows (RB each).  The unit-lower-trapezoidal
+// reflector block of the CTA's rows is staged once in shared memory and serves both GEMMs; the 32 x 16 partial products
+// V^T C meet through distributed shared memory and are summed in CTA order (deterministic).
+__global__ void __launch_bounds__(ATHREADS, 1) qr_apply_kernel(const double* __restrict__ Wv, int ldv, int m, int j0, int nbp,
                                                                const double* __restrict__ T, int transT, double* __restrict__ Cm,
-                                                               int ldc, int c_begin, int c_end) {
+                                                               int ldc, int c_begin, int c_end, int RB) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CR = (int)cluster.num_blocks(), cr = (int)cluster.block_rank();
   extern __shared__ __align__(16) double sm_apply[];
-  double* Tsm = sm_apply;                                               // 32 x 32
-  double (*Wpart)[QNB * QNC] = reinterpret_cast<double (*)[QNB * QNC]>(Tsm + QNB * QNB);  // per-warp partial V^T C
-  double* Wfull = Tsm + QNB * QNB + QWARPS * QNB * QNC;
-  double* W2 = Wfull + QNB * QNC;                                       // holds -op(T) V^T C
+  double* Tsm = sm_apply;                                   // 32 x 32
+  double* Wpart = Tsm + QNB * QNB;                          // [AWARPS][512] per-warp partial V^T C
+  double* Wex = Wpart + AWARPS * QNB * QNC;                 // [QMAXC][512] cluster exchange
+  double* W2 = Wex + QMAXC * QNB * QNC;                     // 512: -op(T) V^T C
+  double* Vs = W2 + QNB * QNC;                              // RB x AVP reflector rows of this CTA
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int c0 = c_begin + blockIdx.x * QNC;
-  const int rows_total = m - j0;
-  for (int idx = tid; idx < QNB * QNB; idx += QTHREADS) Tsm[idx] = T[idx];
+  const int strip = blockIdx.x / CR;
+  const int c0 = c_begin + strip * QNC;
+  const int row0 = j0 + cr * RB;                            // first global row of this CTA
+  const int nrows = max(0, min(RB, m - row0));
+  for (int idx = tid; idx < QNB * QNB; idx += ATHREADS) Tsm[idx] = T[idx];
+  for (int idx = tid; idx < nrows * QNB; idx += ATHREADS) {
+    const int r = idx >> 5, k = idx & 31, rl = row0 + r - j0;  // rl: panel row
+    double v = 0.0;
+    if (k < nbp) v = rl > k ? Wv[(size_t)(row0 + r) * ldv + j0 + k] : (rl == k ? 1.0 : 0.0);
+    Vs[r * AVP + k] = v;
+  }
+  if (CR > 1) cluster.sync();  // peers are resident (remote writes below); doubles as the CTA barrier
+  else __syncthreads();
 
-  // ---- phase 1: W = V^T C  (M = 32 reflectors, N = 16 columns, K = rows; each warp owns every 16th group of 4 rows) ----
+  // ---- phase 1: W = V^T C over this CTA's rows (M = 32 reflectors, N = 16, K = rows; warps take groups of 4 rows) ----
   double acc[4][QNC / 8][2];
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
     for (int nt = 0; nt < QNC / 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-  const int n_quads = (rows_total + 3) / 4;
-  for (int q = warp; q < n_quads; q += QWARPS) {
-    const int r = j0 + 4 * q + t;
+  const int n_quads = (nrows + 3) / 4;
+  for (int q = warp; q < n_quads; q += AWARPS) {
+    const int r = 4 * q + t;  // local row
     double a[4], b[QNC / 8];
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt) a[mt] = qr_vload(Wv, ldv, m, j0, nbp, r, 8 * mt + g);
 #pragma unroll
     for (int nt = 0; nt < QNC / 8; ++nt) {
       const int cc = c0 + 8 * nt + g;
-      b[nt] = (r < m && cc < c_end) ? Cm[(size_t)r * ldc + cc] : 0.0;
+      b[nt] = (r < nrows && cc < c_end) ? Cm[(size_t)(row0 + r) * ldc + cc] : 0.0;
     }
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) a[mt] = r < nrows ? Vs[r * AVP + 8 * mt + g] : 0.0;
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
@@ -214,52 +242,63 @@ __global__ void __launch_bounds__(QTHREADS, 1) qr_apply_kernel(const double* __r
   for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
     for (int nt = 0; nt < QNC / 8; ++nt) {
-      Wpart[warp][(8 * mt + g) * QNC + 8 * nt + 2 * t] = acc[mt][nt][0];
-      Wpart[warp][(8 * mt + g) * QNC + 8 * nt + 2 * t + 1] = acc[mt][nt][1];
+      Wpart[warp * (QNB * QNC) + (8 * mt + g) * QNC + 8 * nt + 2 * t] = acc[mt][nt][0];
+      Wpart[warp * (QNB * QNC) + (8 * mt + g) * QNC + 8 * nt + 2 * t + 1] = acc[mt][nt][1];
     }
   __syncthreads();
-  {
+  for (int e = tid; e < QNB * QNC; e += ATHREADS) {
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < QWARPS; ++w) s += Wpart[w][tid];  // QNB * QNC == QTHREADS
-    Wfull[tid] = s;
+    for (int w = 0; w < AWARPS; ++w) s += Wpart[w * (QNB * QNC) + e];
+    if (CR == 1) {
+      Wex[e] = s;
+    } else {
+      for (int dst = 0; dst < CR; ++dst) cluster.map_shared_rank(Wex, dst)[cr * (QNB * QNC) + e] = s;
+    }
+  }
+  if (CR > 1) cluster.sync(); else __syncthreads();
+  for (int e = tid; e < QNB * QNC; e += ATHREADS) {  // total over the CTAs in rank order, kept in Wpart[0..512)
+    double s = 0.0;
+    for (int src = 0; src < CR; ++src) s += Wex[src * (QNB * QNC) + e];
+    Wpart[e] = s;
   }
   __syncthreads();
-  {
-    const int i = tid / QNC, cc = tid % QNC;
+  for (int e = tid; e < QNB * QNC; e += ATHREADS) {
+    const int i = e / QNC, cc = e % QNC;
     double s = 0.0;
     if (transT) {
-      for (int k = 0; k <= i; ++k) s += Tsm[k * QNB + i] * Wfull[k * QNC + cc];
+      for (int k = 0; k <= i; ++k) s += Tsm[k * QNB + i] * Wpart[k * QNC + cc];
     } else {
-      for (int k = i; k < QNB; ++k) s += Tsm[i * QNB + k] * Wfull[k * QNC + cc];
+      for (int k = i; k < QNB; ++k) s += Tsm[i * QNB + k] * Wpart[k * QNC + cc];
     }
-    W2[tid] = -s;
+    W2[e] = -s;
   }
   __syncthreads();
-  // ---- phase 2: C += V W2  (M = rows, N = 16, K = 32; each warp owns every 16th group of 8 rows) ----
-  const int n_oct = (rows_total + 7) / 8;
-  for (int o = warp; o < n_oct; o += QWARPS) {
-    const int r = j0 + 8 * o + g;
+  // ---- phase 2: C += V W2 on this CTA's rows (M = rows, N = 16, K = 32; warps take groups of 8 rows) ----
+  const int n_oct = (nrows + 7) / 8;
+  for (int o = warp; o < n_oct; o += AWARPS) {
+    const int r = 8 * o + g;
     double cacc[QNC / 8][2];
 #pragma unroll
     for (int nt = 0; nt < QNC / 8; ++nt) {
       const int cc = c0 + 8 * nt + 2 * t;
-      cacc[nt][0] = (r < m && cc < c_end) ? Cm[(size_t)r * ldc + cc] : 0.0;
-      cacc[nt][1] = (r < m && cc + 1 < c_end) ? Cm[(size_t)r * ldc + cc + 1] : 0.0;
+      cacc[nt][0] = (r < nrows && cc < c_end) ? Cm[(size_t)(row0 + r) * ldc + cc] : 0.0;
+      cacc[nt][1] = (r < nrows && cc + 1 < c_end) ? Cm[(size_t)(row0 + r) * ldc + cc + 1] : 0.0;
     }
 #pragma unroll
     for (int ks = 0; ks < QNB / 4; ++ks) {
-      const double a = qr_vload(Wv, ldv, m, j0, nbp, r, 4 * ks + t);
+      const double a = r < nrows ? Vs[r * AVP + 4 * ks + t] : 0.0;
 #pragma unroll
       for (int nt = 0; nt < QNC / 8; ++nt) dmma884(cacc[nt], a, W2[(4 * ks + t) * QNC + 8 * nt + g]);
     }
 #pragma unroll
     for (int nt = 0; nt < QNC / 8; ++nt) {
       const int cc = c0 + 8 * nt + 2 * t;
-      if (r < m && cc < c_end) Cm[(size_t)r * ldc + cc] = cacc[nt][0];
-      if (r < m && cc + 1 < c_end) Cm[(size_t)r * ldc + cc + 1] = cacc[nt][1];
+      if (r < nrows && cc < c_end) Cm[(size_t)(row0 + r) * ldc + cc] = cacc[nt][0];
+      if (r < nrows && cc + 1 < c_end) Cm[(size_t)(row0 + r) * ldc + cc + 1] = cacc[nt][1];
     }
   }
+  if (CR > 1) cluster.sync();  // no CTA exits while a peer may still write its exchange slots
 }
 
 // out (rows x cols, ld ldo) = in^T or in;  tiled through shared memory
@@ -299,23 +338,12 @@ __global__ void qr_eye_kernel(double* __restrict__ Q, int m, int k) {
 
 static int grid_for(long long n) { return (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8); }
 
-static int launch_panel(double* W, int ld, int m, int j0, int nbp, double* tau, double* T, cudaStream_t stream) {
-  const int rows = m - j0;
-  int C = 1;
-  while (C < QMAXC && (rows + C - 1) / C > 256 && rows / (2 * C) >= QNB) C *= 2;
-  int R = ((rows + C - 1) / C + 7) / 8 * 8;
-  TN_REQUIRE(R <= QMAX_ROWS_PER_CTA, "tn_qr: %d rows exceed the panel capacity (%d rows)", rows, QMAXC * QMAX_ROWS_PER_CTA);
-  TN_REQUIRE(C == 1 || R >= QNB, "tn_qr: internal panel split");
-  const size_t smem = panel_smem_bytes(R);
-  static size_t configured = 0;
-  if (smem > configured) {
-    TN_CUDA(cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem_bytes(QMAX_ROWS_PER_CTA)));
-    configured = panel_smem_bytes(QMAX_ROWS_PER_CTA);
-  }
+template <int RPT>
+static int launch_panel_t(double* W, int ld, int m, int j0, int nbp, double* tau, double* T, int C, cudaStream_t stream) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(C);
   cfg.blockDim = dim3(QTHREADS);
-  cfg.dynamicSmemBytes = smem;
+  cfg.dynamicSmemBytes = 0;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -324,22 +352,59 @@ static int launch_panel(double* W, int ld, int m, int j0, int nbp, double* tau, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  TN_CUDA(cudaLaunchKernelEx(&cfg, qr_panel_kernel, W, ld, m, j0, nbp, tau, T, R));
+  TN_CUDA(cudaLaunchKernelEx(&cfg, qr_panel_kernel<RPT>, W, ld, m, j0, nbp, tau, T));
   TN_LAUNCHED();
   return TN_OK;
+}
+
+static int launch_panel(double* W, int ld, int m, int j0, int nbp, double* tau, double* T, cudaStream_t stream) {
+  const int rows = m - j0;
+  // one CTA holds up to 768 rows in registers; more rows are spread over a cluster of 2 / 4 / 8 CTAs (512 rows each when possible)
+  int C = 1;
+  if (rows > QMAX_RPT * QWARPS) {
+    C = 2;
+    while (C < QMAXC && (rows + C - 1) / C > 512) C *= 2;
+  }
+  const int per_cta = (rows + C - 1) / C;
+  const int rpt = (per_cta + QWARPS - 1) / QWARPS;
+  TN_REQUIRE(rpt <= QMAX_RPT, "tn_qr: %d rows exceed the panel capacity (%d rows)", rows, QMAXC * QMAX_RPT * QWARPS);
+  TN_REQUIRE(C == 1 || per_cta >= QNB, "tn_qr: internal panel split");
+  if (rpt <= 2) return launch_panel_t<2>(W, ld, m, j0, nbp, tau, T, C, stream);
+  if (rpt <= 4) return launch_panel_t<4>(W, ld, m, j0, nbp, tau, T, C, stream);
+  if (rpt <= 8) return launch_panel_t<8>(W, ld, m, j0, nbp, tau, T, C, stream);
+  if (rpt <= 16) return launch_panel_t<16>(W, ld, m, j0, nbp, tau, T, C, stream);
+  if (rpt <= 32) return launch_panel_t<32>(W, ld, m, j0, nbp, tau, T, C, stream);
+  return launch_panel_t<QMAX_RPT>(W, ld, m, j0, nbp, tau, T, C, stream);
 }
 
 static int launch_apply(const double* Wv, int ldv, int m, int j0, int nbp, const double* T, int transT, double* Cm, int ldc,
                         int c_begin, int c_end, cudaStream_t stream) {
   if (c_end <= c_begin || m - j0 <= 0) return TN_OK;
+  const int rows = m - j0;
   const int strips = (c_end - c_begin + QNC - 1) / QNC;
-  constexpr size_t smem = sizeof(double) * (QNB * QNB + QWARPS * QNB * QNC + 2 * QNB * QNC);
-  static bool configured = false;
-  if (!configured) {
-    TN_CUDA(cudaFuncSetAttribute(qr_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+  int CR = 1;
+  while (CR < QMAXC && (rows + CR - 1) / CR > 256) CR *= 2;
+  const int RB = ((rows + CR - 1) / CR + 7) / 8 * 8;
+  const size_t smem = sizeof(double) * ((size_t)QNB * QNB + (size_t)AWARPS * QNB * QNC + (size_t)QMAXC * QNB * QNC + (size_t)QNB * QNC + (size_t)RB * AVP);
+  TN_REQUIRE(smem <= 227 * 1024, "tn_qr: %d rows exceed the apply capacity", rows);
+  static size_t configured = 0;
+  if (smem > configured) {
+    TN_CUDA(cudaFuncSetAttribute(qr_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = 227 * 1024;
   }
-  qr_apply_kernel<<<strips, QTHREADS, smem, stream>>>(Wv, ldv, m, j0, nbp, T, transT, Cm, ldc, c_begin, c_end);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(strips * CR);
+  cfg.blockDim = dim3(ATHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CR;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TN_CUDA(cudaLaunchKernelEx(&cfg, qr_apply_kernel, Wv, ldv, m, j0, nbp, T, transT, Cm, ldc, c_begin, c_end, RB));
   TN_LAUNCHED();
   return TN_OK;
 }
