@@ -359,9 +359,9 @@ static int launch_panel_t(double* W, int ld, int m, int j0, int nbp, double* tau
 
 static int launch_panel(double* W, int ld, int m, int j0, int nbp, double* tau, double* T, cudaStream_t stream) {
   const int rows = m - j0;
-  // one CTA holds up to 768 rows in registers; more rows are spread over a cluster of 2 / 4 / 8 CTAs (512 rows each when possible)
+  // one CTA holds up to 512 rows in registers without spilling (768 with); more rows are spread over a cluster of 2 / 4 / 8 CTAs
   int C = 1;
-  if (rows > QMAX_RPT * QWARPS) {
+  if (rows > 512) {
     C = 2;
     while (C < QMAXC && (rows + C - 1) / C > 512) C *= 2;
   }
