@@ -55,7 +55,7 @@ __device__ __forceinline__ double warp_sum_q(double v) {
 // column-j broadcast is a warp shuffle and the rank-1 update touches registers only; shared memory carries just the
 // cross-warp / cross-CTA partial sums (double-buffered by the parity of j: ONE CTA barrier -- plus one cluster barrier when
 // the panel spans several CTAs -- per column).
-template <int RPT>
+template <int RPT, bool KEEP>
 __global__ void __launch_bounds__(QTHREADS, 1) qr_panel_kernel(double* __restrict__ W, int ld, int m, int j0, int nbp,
                                                                double* __restrict__ tau_out, double* __restrict__ T_out) {
   cg::cluster_group cluster = cg::this_cluster();
@@ -87,11 +87,13 @@ __global__ void __launch_bounds__(QTHREADS, 1) qr_panel_kernel(double* __restric
   for (int j = 0; j < nbp; ++j) {
     const int par = j & 1;
     // ---- row j of the panel Gram matrix, g_k = sum_{rows >= j} P[r,j] P[r,k], over this thread's rows ----
+    double xjs[KEEP ? RPT : 1];  // column j of this thread's rows (one warp shuffle per row; reused by the update when KEEP)
     {
       double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
       for (int i = 0; i < RPT; ++i) {
         const double xj = __shfl_sync(0xffffffffu, x[i], j);
+        if (KEEP) xjs[i] = xj;
         const double pr = (row_lo + i * QWARPS + warp >= j) ? xj * x[i] : 0.0;
         if (i & 1) acc1 += pr; else acc0 += pr;
       }
@@ -135,17 +137,23 @@ __global__ void __launch_bounds__(QTHREADS, 1) qr_panel_kernel(double* __restric
     if (rows_total - 1 - j == 0 || !(gj > 1e-280)) {
       tau = 0.0; beta = alpha; scale = 0.0;
     } else {
-      const double nrm = sqrt(gj);
+      // beta = -sign(alpha) |x|, tau = (beta - alpha) / beta = 1 + |alpha| / |x|, scale = 1 / (alpha - beta): one rsqrt and one
+      // reciprocal instead of a square root and two divisions on the critical path of the column
+      double rn = rsqrt(gj);
+      rn = rn * (1.5 - 0.5 * gj * rn * rn);   // one Newton step: full double precision whatever rsqrt's last bit does
+      const double nrm = gj * rn;
+      const double aabs = fabs(alpha);
       beta = alpha >= 0.0 ? -nrm : nrm;
-      tau = (beta - alpha) / beta;
-      scale = 1.0 / (alpha - beta);
+      tau = 1.0 + aabs * rn;
+      const double inv = 1.0 / (aabs + nrm);
+      scale = alpha >= 0.0 ? inv : -inv;
     }
     const double y = (gk - beta * rjk) * scale;  // k > j: v^T a_k;  k < j: V_k^T v_j
     const double ty = tau * y;
     // ---- apply H_j to the columns k > j (registers only), store v below the diagonal and beta on it ----
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
-      const double xj = __shfl_sync(0xffffffffu, x[i], j);
+      const double xj = KEEP ? xjs[i] : __shfl_sync(0xffffffffu, x[i], j);
       const int pr = row_lo + i * QWARPS + warp;
       if (pr > j) {
         const double vr = xj * scale;
@@ -206,12 +214,24 @@ __global__ void __launch_bounds__(ATHREADS, 1) qr_apply_kernel(const double* __r
   const int c0 = c_begin + strip * QNC;
   const int row0 = j0 + cr * RB;                            // first global row of this CTA
   const int nrows = max(0, min(RB, m - row0));
-  for (int idx = tid; idx < QNB * QNB; idx += ATHREADS) Tsm[idx] = T[idx];
-  for (int idx = tid; idx < nrows * QNB; idx += ATHREADS) {
-    const int r = idx >> 5, k = idx & 31, rl = row0 + r - j0;  // rl: panel row
-    double v = 0.0;
-    if (k < nbp) v = rl > k ? Wv[(size_t)(row0 + r) * ldv + j0 + k] : (rl == k ? 1.0 : 0.0);
-    Vs[r * AVP + k] = v;
+#pragma unroll
+  for (int u = 0; u < QNB * QNB / ATHREADS; ++u) Tsm[tid + u * ATHREADS] = T[tid + u * ATHREADS];
+  // reflector rows of this CTA: batches of 8 independent loads per thread (a plain loop would serialise the L2 latency)
+  for (int base = 0; base < nrows * QNB; base += 8 * ATHREADS) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * ATHREADS + tid;
+      const int r = idx >> 5, k = idx & 31;
+      const bool in = idx < nrows * QNB && k < nbp && (row0 + r - j0) > k;
+      v[u] = in ? Wv[(size_t)(row0 + r) * ldv + j0 + k] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * ATHREADS + tid;
+      const int r = idx >> 5, k = idx & 31;
+      if (idx < nrows * QNB) Vs[r * AVP + k] = (k < nbp && (row0 + r - j0) == k) ? 1.0 : v[u];
+    }
   }
   if (CR > 1) cluster.sync();  // peers are resident (remote writes below); doubles as the CTA barrier
   else __syncthreads();
@@ -223,20 +243,31 @@ __global__ void __launch_bounds__(ATHREADS, 1) qr_apply_kernel(const double* __r
 #pragma unroll
     for (int nt = 0; nt < QNC / 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
   const int n_quads = (nrows + 3) / 4;
-  for (int q = warp; q < n_quads; q += AWARPS) {
-    const int r = 4 * q + t;  // local row
-    double a[4], b[QNC / 8];
+  constexpr int UQ = 8;  // row groups per batch: their C operands are loaded together
+  for (int q0 = warp; q0 < n_quads; q0 += UQ * AWARPS) {
+    double b[UQ][QNC / 8];
 #pragma unroll
-    for (int nt = 0; nt < QNC / 8; ++nt) {
-      const int cc = c0 + 8 * nt + g;
-      b[nt] = (r < nrows && cc < c_end) ? Cm[(size_t)(row0 + r) * ldc + cc] : 0.0;
+    for (int u = 0; u < UQ; ++u) {
+      const int r = 4 * (q0 + u * AWARPS) + t;  // local row
+#pragma unroll
+      for (int nt = 0; nt < QNC / 8; ++nt) {
+        const int cc = c0 + 8 * nt + g;
+        b[u][nt] = (r < nrows && cc < c_end) ? Cm[(size_t)(row0 + r) * ldc + cc] : 0.0;
+      }
     }
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt) a[mt] = r < nrows ? Vs[r * AVP + 8 * mt + g] : 0.0;
+    for (int u = 0; u < UQ; ++u) {
+      const int r = 4 * (q0 + u * AWARPS) + t;
+      if (4 * (q0 + u * AWARPS) < nrows) {  // warp-uniform
+        double a[4];
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
+        for (int mt = 0; mt < 4; ++mt) a[mt] = r < nrows ? Vs[r * AVP + 8 * mt + g] : 0.0;
 #pragma unroll
-      for (int nt = 0; nt < QNC / 8; ++nt) dmma884(acc[mt][nt], a[mt], b[nt]);
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < QNC / 8; ++nt) dmma884(acc[mt][nt], a[mt], b[u][nt]);
+      }
+    }
   }
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt)
@@ -276,26 +307,41 @@ __global__ void __launch_bounds__(ATHREADS, 1) qr_apply_kernel(const double* __r
   __syncthreads();
   // ---- phase 2: C += V W2 on this CTA's rows (M = rows, N = 16, K = 32; warps take groups of 8 rows) ----
   const int n_oct = (nrows + 7) / 8;
-  for (int o = warp; o < n_oct; o += AWARPS) {
-    const int r = 8 * o + g;
-    double cacc[QNC / 8][2];
+  constexpr int UO = 4;  // row groups per batch
+  for (int o0 = warp; o0 < n_oct; o0 += UO * AWARPS) {
+    double cacc[UO][QNC / 8][2];
 #pragma unroll
-    for (int nt = 0; nt < QNC / 8; ++nt) {
-      const int cc = c0 + 8 * nt + 2 * t;
-      cacc[nt][0] = (r < nrows && cc < c_end) ? Cm[(size_t)(row0 + r) * ldc + cc] : 0.0;
-      cacc[nt][1] = (r < nrows && cc + 1 < c_end) ? Cm[(size_t)(row0 + r) * ldc + cc + 1] : 0.0;
+    for (int u = 0; u < UO; ++u) {
+      const int r = 8 * (o0 + u * AWARPS) + g;
+#pragma unroll
+      for (int nt = 0; nt < QNC / 8; ++nt) {
+        const int cc = c0 + 8 * nt + 2 * t;
+        cacc[u][nt][0] = (r < nrows && cc < c_end) ? Cm[(size_t)(row0 + r) * ldc + cc] : 0.0;
+        cacc[u][nt][1] = (r < nrows && cc + 1 < c_end) ? Cm[(size_t)(row0 + r) * ldc + cc + 1] : 0.0;
+      }
     }
 #pragma unroll
     for (int ks = 0; ks < QNB / 4; ++ks) {
-      const double a = r < nrows ? Vs[r * AVP + 4 * ks + t] : 0.0;
+      double bw[QNC / 8];
 #pragma unroll
-      for (int nt = 0; nt < QNC / 8; ++nt) dmma884(cacc[nt], a, W2[(4 * ks + t) * QNC + 8 * nt + g]);
+      for (int nt = 0; nt < QNC / 8; ++nt) bw[nt] = W2[(4 * ks + t) * QNC + 8 * nt + g];
+#pragma unroll
+      for (int u = 0; u < UO; ++u) {
+        const int r = 8 * (o0 + u * AWARPS) + g;
+        const double a = r < nrows ? Vs[r * AVP + 4 * ks + t] : 0.0;
+#pragma unroll
+        for (int nt = 0; nt < QNC / 8; ++nt) dmma884(cacc[u][nt], a, bw[nt]);
+      }
     }
 #pragma unroll
-    for (int nt = 0; nt < QNC / 8; ++nt) {
-      const int cc = c0 + 8 * nt + 2 * t;
-      if (r < nrows && cc < c_end) Cm[(size_t)(row0 + r) * ldc + cc] = cacc[nt][0];
-      if (r < nrows && cc + 1 < c_end) Cm[(size_t)(row0 + r) * ldc + cc + 1] = cacc[nt][1];
+    for (int u = 0; u < UO; ++u) {
+      const int r = 8 * (o0 + u * AWARPS) + g;
+#pragma unroll
+      for (int nt = 0; nt < QNC / 8; ++nt) {
+        const int cc = c0 + 8 * nt + 2 * t;
+        if (r < nrows && cc < c_end) Cm[(size_t)(row0 + r) * ldc + cc] = cacc[u][nt][0];
+        if (r < nrows && cc + 1 < c_end) Cm[(size_t)(row0 + r) * ldc + cc + 1] = cacc[u][nt][1];
+      }
     }
   }
   if (CR > 1) cluster.sync();  // no CTA exits while a peer may still write its exchange slots
@@ -338,7 +384,7 @@ __global__ void qr_eye_kernel(double* __restrict__ Q, int m, int k) {
 
 static int grid_for(long long n) { return (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8); }
 
-template <int RPT>
+template <int RPT, bool KEEP>
 static int launch_panel_t(double* W, int ld, int m, int j0, int nbp, double* tau, double* T, int C, cudaStream_t stream) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(C);
@@ -352,29 +398,27 @@ static int launch_panel_t(double* W, int ld, int m, int j0, int nbp, double* tau
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  TN_CUDA(cudaLaunchKernelEx(&cfg, qr_panel_kernel<RPT>, W, ld, m, j0, nbp, tau, T));
+  TN_CUDA(cudaLaunchKernelEx(&cfg, qr_panel_kernel<RPT, KEEP>, W, ld, m, j0, nbp, tau, T));
   TN_LAUNCHED();
   return TN_OK;
 }
 
 static int launch_panel(double* W, int ld, int m, int j0, int nbp, double* tau, double* T, cudaStream_t stream) {
   const int rows = m - j0;
-  // one CTA holds up to 512 rows in registers without spilling (768 with); more rows are spread over a cluster of 2 / 4 / 8 CTAs
+  // 256 rows per CTA (16 per thread: the column-j broadcast of a row costs one shuffle per column) while a cluster of up to 8
+  // CTAs covers the panel; taller panels put more rows into each thread (up to 768 per CTA, 6144 per cluster)
   int C = 1;
-  if (rows > 512) {
-    C = 2;
-    while (C < QMAXC && (rows + C - 1) / C > 512) C *= 2;
-  }
+  while (C < QMAXC && (rows + C - 1) / C > 256 && rows / (2 * C) >= QNB) C *= 2;
   const int per_cta = (rows + C - 1) / C;
   const int rpt = (per_cta + QWARPS - 1) / QWARPS;
   TN_REQUIRE(rpt <= QMAX_RPT, "tn_qr: %d rows exceed the panel capacity (%d rows)", rows, QMAXC * QMAX_RPT * QWARPS);
   TN_REQUIRE(C == 1 || per_cta >= QNB, "tn_qr: internal panel split");
-  if (rpt <= 2) return launch_panel_t<2>(W, ld, m, j0, nbp, tau, T, C, stream);
-  if (rpt <= 4) return launch_panel_t<4>(W, ld, m, j0, nbp, tau, T, C, stream);
-  if (rpt <= 8) return launch_panel_t<8>(W, ld, m, j0, nbp, tau, T, C, stream);
-  if (rpt <= 16) return launch_panel_t<16>(W, ld, m, j0, nbp, tau, T, C, stream);
-  if (rpt <= 32) return launch_panel_t<32>(W, ld, m, j0, nbp, tau, T, C, stream);
-  return launch_panel_t<QMAX_RPT>(W, ld, m, j0, nbp, tau, T, C, stream);
+  if (rpt <= 2) return launch_panel_t<2, true>(W, ld, m, j0, nbp, tau, T, C, stream);
+  if (rpt <= 4) return launch_panel_t<4, true>(W, ld, m, j0, nbp, tau, T, C, stream);
+  if (rpt <= 8) return launch_panel_t<8, true>(W, ld, m, j0, nbp, tau, T, C, stream);
+  if (rpt <= 16) return launch_panel_t<16, true>(W, ld, m, j0, nbp, tau, T, C, stream);
+  if (rpt <= 32) return launch_panel_t<32, false>(W, ld, m, j0, nbp, tau, T, C, stream);
+  return launch_panel_t<QMAX_RPT, false>(W, ld, m, j0, nbp, tau, T, C, stream);
 }
 
 static int launch_apply(const double* Wv, int ldv, int m, int j0, int nbp, const double* T, int transT, double* Cm, int ldc,
