@@ -13,9 +13,9 @@
 //                     which the column norm (k = j), the reflector products v^T a_k (k > j) and the entries V_k^T v_j of the
 //                     compact-WY factor T (k < j) all follow:  y_k = (g_k - beta P[j,k]) / (alpha - beta).
 //                     Latency per column = one CTA barrier + one cluster barrier (~0.5 us), not a chain of launches.
-//   qr_apply_kernel   C <- (1 - V op(T) V^T) C on a strip of 16 columns per CTA with FP64 tensor-core MMAs (DMMA.8x8x4):
-//                     W = V^T C (warps split the rows, fixed-order reduction through shared memory), W <- op(T) W,
-//                     C -= V W.  Used for the trailing update (op(T) = T^T) and for forming Q (op(T) = T, panels in reverse).
+//   qr_apply_kernel   C <- (1 - V op(T) V^T) C on a strip of 32 columns per cluster (the CTAs split the rows) with FP64
+//                     tensor-core MMAs (DMMA.8x8x4): W = V^T C (partial tiles meet in distributed shared memory, summed in
+//                     CTA order), W <- op(T) W, C -= V W.  Used for the trailing update (op(T) = T^T) and for forming Q (op(T) = T, panels in reverse).
 // No atomics anywhere: results are bit-reproducible (replicas on several GPUs stay identical).
 #include <cooperative_groups.h>
 
@@ -34,7 +34,7 @@ constexpr int QWARPS = QTHREADS / 32;
 constexpr int QMAXC = 8;       // portable cluster size
 constexpr int QSLOT = 2 * QNB; // doubles one CTA contributes per column: g[32], row j[32]
 constexpr int QMAX_RPT = 48;   // rows per thread of the panel kernel -> 768 rows per CTA, 6144 per cluster
-constexpr int QNC = 16;        // strip width of the apply kernel
+constexpr int QNC = 32;        // strip width of the apply kernel
 constexpr int ATHREADS = 256;  // apply kernel: 8 warps
 constexpr int AWARPS = ATHREADS / 32;
 constexpr int AVP = QNB + 4;   // pitch of the reflector block in shared memory (conflict-free fragment reads)
@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(QTHREADS, 1) qr_panel_kernel(double* __restric
   for (int j = 0; j < nbp; ++j) {
     const int par = j & 1;
     // ---- row j of the panel Gram matrix, g_k = sum_{rows >= j} P[r,j] P[r,k], over this thread's rows ----
+    // only the rows of the diagonal block (panel rows < 32: i < 2 of CTA 0) can lie above row j; all others take the plain FMA
     double xjs[KEEP ? RPT : 1];  // column j of this thread's rows (one warp shuffle per row; reused by the update when KEEP)
     {
       double acc0 = 0.0, acc1 = 0.0;
@@ -94,8 +95,9 @@ __global__ void __launch_bounds__(QTHREADS, 1) qr_panel_kernel(double* __restric
       for (int i = 0; i < RPT; ++i) {
         const double xj = __shfl_sync(0xffffffffu, x[i], j);
         if (KEEP) xjs[i] = xj;
-        const double pr = (row_lo + i * QWARPS + warp >= j) ? xj * x[i] : 0.0;
-        if (i & 1) acc1 += pr; else acc0 += pr;
+        double xi = x[i];
+        if (i < 2) xi = (row_lo + i * QWARPS + warp >= j) ? xi : 0.0;
+        if (i & 1) acc1 = fma(xj, xi, acc1); else acc0 = fma(xj, xi, acc0);
       }
       red[par][warp][lane] = acc0 + acc1;
       if (c == 0 && warp == (j & (QWARPS - 1))) rowj[par][lane] = (RPT > 1 && j >= QWARPS) ? x[RPT > 1 ? 1 : 0] : x[0];  // row j = i*16 + warp
@@ -151,17 +153,24 @@ __global__ void __launch_bounds__(QTHREADS, 1) qr_panel_kernel(double* __restric
     const double y = (gk - beta * rjk) * scale;  // k > j: v^T a_k;  k < j: V_k^T v_j
     const double ty = tau * y;
     // ---- apply H_j to the columns k > j (registers only), store v below the diagonal and beta on it ----
+    // x[r,k] -= (tau y_k scale) x[r,j] for k > j: the coefficient is zero in the lanes k <= j, so rows below the diagonal block
+    // need one FMA and one predicated multiply (lane j: v_r = x[r,j] scale) with no branch
+    const double coef = lane > j ? ty * scale : 0.0;
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
       const double xj = KEEP ? xjs[i] : __shfl_sync(0xffffffffu, x[i], j);
-      const int pr = row_lo + i * QWARPS + warp;
-      if (pr > j) {
-        const double vr = xj * scale;
-        if (lane > j) x[i] -= ty * vr;
-        else if (lane == j) x[i] = vr;
-      } else if (pr == j) {
-        if (lane > j) x[i] -= ty;
-        else if (lane == j) x[i] = beta;
+      if (i < 2) {
+        const int pr = row_lo + i * QWARPS + warp;
+        if (pr > j) {
+          x[i] = fma(-coef, xj, x[i]);
+          if (lane == j) x[i] = xj * scale;
+        } else if (pr == j) {
+          if (lane > j) x[i] -= ty;
+          else if (lane == j) x[i] = beta;
+        }
+      } else {
+        x[i] = fma(-coef, xj, x[i]);
+        if (lane == j) x[i] = xj * scale;
       }
     }
     if (c == 0 && warp == (j & (QWARPS - 1))) {  // the warp that owns row j records the T-factor inputs
@@ -195,20 +204,23 @@ __global__ void __launch_bounds__(QTHREADS, 1) qr_panel_kernel(double* __restric
 }
 
 // Cm[j0:m, c_begin:c_end] <- (1 - V op(T) V^T) Cm[j0:m, c_begin:c_end];  transT != 0: op(T) = T^T.
-// One cluster per strip of 16 columns; the CTAs of the cluster split the rows (RB each).  The unit-lower-trapezoidal
-// reflector block of the CTA's rows is staged once in shared memory and serves both GEMMs; the 32 x 16 partial products
-// V^T C meet through distributed shared memory and are summed in CTA order (deterministic).
+// One cluster per strip of QNC = 32 columns; the CTAs of the cluster split the rows (RB each).  The unit-lower-trapezoidal
+// reflector block of the CTA's rows is staged once in shared memory and serves both GEMMs.  Phase 1 (W = V^T C): warp w owns
+// the 8 x 16 output tile (reflectors 8*(w%4).., columns 16*(w/4)..) over all rows of the CTA -- no cross-warp reduction; the
+// CTAs' partial tiles meet through distributed shared memory and are summed in CTA order (deterministic).  Phase 2: C -= V W.
 __global__ void __launch_bounds__(ATHREADS, 1) qr_apply_kernel(const double* __restrict__ Wv, int ldv, int m, int j0, int nbp,
                                                                const double* __restrict__ T, int transT, double* __restrict__ Cm,
-                                                               int ldc, int c_begin, int c_end, int RB) {
+                                                               int ldc, int c_begin, int c_end, int RB, int vp) {
+  // vp: pitch of the staged reflector rows (36 conflict-free, 32 when the padded block would not fit); 0: not staged, read from global
   cg::cluster_group cluster = cg::this_cluster();
   const int CR = (int)cluster.num_blocks(), cr = (int)cluster.block_rank();
   extern __shared__ __align__(16) double sm_apply[];
+  constexpr int WSZ = QNB * QNC;                            // 32 x 32 block of V^T C
   double* Tsm = sm_apply;                                   // 32 x 32
-  double* Wpart = Tsm + QNB * QNB;                          // [AWARPS][512] per-warp partial V^T C
-  double* Wex = Wpart + AWARPS * QNB * QNC;                 // [QMAXC][512] cluster exchange
-  double* W2 = Wex + QMAXC * QNB * QNC;                     // 512: -op(T) V^T C
-  double* Vs = W2 + QNB * QNC;                              // RB x AVP reflector rows of this CTA
+  double* Wex = Tsm + QNB * QNB;                            // [QMAXC][WSZ] cluster exchange
+  double* Wtot = Wex + QMAXC * WSZ;                         // WSZ: sum over the CTAs
+  double* W2 = Wtot + WSZ;                                  // WSZ: -op(T) V^T C
+  double* Vs = W2 + WSZ;                                    // RB x vp reflector rows of this CTA
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int strip = blockIdx.x / CR;
   const int c0 = c_begin + strip * QNC;
@@ -216,8 +228,13 @@ __global__ void __launch_bounds__(ATHREADS, 1) qr_apply_kernel(const double* __r
   const int nrows = max(0, min(RB, m - row0));
 #pragma unroll
   for (int u = 0; u < QNB * QNB / ATHREADS; ++u) Tsm[tid + u * ATHREADS] = T[tid + u * ATHREADS];
+  auto vglobal = [&](int r, int k) -> double {  // unit-lower-trapezoidal reflector entry of local row r (not staged)
+    const int rl = row0 + r - j0;
+    if (r >= nrows || k >= nbp || rl < k) return 0.0;
+    return rl == k ? 1.0 : Wv[(size_t)(row0 + r) * ldv + j0 + k];
+  };
   // reflector rows of this CTA: batches of 8 independent loads per thread (a plain loop would serialise the L2 latency)
-  for (int base = 0; base < nrows * QNB; base += 8 * ATHREADS) {
+  for (int base = 0; vp > 0 && base < nrows * QNB; base += 8 * ATHREADS) {
     double v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -230,84 +247,76 @@ __global__ void __launch_bounds__(ATHREADS, 1) qr_apply_kernel(const double* __r
     for (int u = 0; u < 8; ++u) {
       const int idx = base + u * ATHREADS + tid;
       const int r = idx >> 5, k = idx & 31;
-      if (idx < nrows * QNB) Vs[r * AVP + k] = (k < nbp && (row0 + r - j0) == k) ? 1.0 : v[u];
+      if (idx < nrows * QNB) Vs[r * vp + k] = (k < nbp && (row0 + r - j0) == k) ? 1.0 : v[u];
     }
   }
   if (CR > 1) cluster.sync();  // peers are resident (remote writes below); doubles as the CTA barrier
   else __syncthreads();
 
-  // ---- phase 1: W = V^T C over this CTA's rows (M = 32 reflectors, N = 16, K = rows; warps take groups of 4 rows) ----
-  double acc[4][QNC / 8][2];
+  // ---- phase 1: tile (mt, 2 n-tiles) of W = V^T C over all rows of this CTA; 4 interleaved accumulators per tile ----
+  {
+    const int mt = warp & 3, nh = warp >> 2;                // reflectors 8*mt.., columns 16*nh..
+    double acc[4][2][2];
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt)
+    for (int u = 0; u < 4; ++u)
 #pragma unroll
-    for (int nt = 0; nt < QNC / 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-  const int n_quads = (nrows + 3) / 4;
-  constexpr int UQ = 8;  // row groups per batch: their C operands are loaded together
-  for (int q0 = warp; q0 < n_quads; q0 += UQ * AWARPS) {
-    double b[UQ][QNC / 8];
+      for (int nt = 0; nt < 2; ++nt) acc[u][nt][0] = acc[u][nt][1] = 0.0;
+    const int n_quads = (nrows + 3) / 4;
+    for (int q0 = 0; q0 < n_quads; q0 += 8) {
+      double b[8][2], a[8];
 #pragma unroll
-    for (int u = 0; u < UQ; ++u) {
-      const int r = 4 * (q0 + u * AWARPS) + t;  // local row
+      for (int u = 0; u < 8; ++u) {
+        const int r = 4 * (q0 + u) + t;  // local row
 #pragma unroll
-      for (int nt = 0; nt < QNC / 8; ++nt) {
-        const int cc = c0 + 8 * nt + g;
-        b[u][nt] = (r < nrows && cc < c_end) ? Cm[(size_t)(row0 + r) * ldc + cc] : 0.0;
+        for (int nt = 0; nt < 2; ++nt) {
+          const int cc = c0 + 16 * nh + 8 * nt + g;
+          b[u][nt] = (r < nrows && cc < c_end) ? Cm[(size_t)(row0 + r) * ldc + cc] : 0.0;
+        }
+        a[u] = vp > 0 ? (r < nrows ? Vs[r * vp + 8 * mt + g] : 0.0) : vglobal(r, 8 * mt + g);
       }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) dmma884(acc[u & 3][nt], a[u], b[u][nt]);
     }
 #pragma unroll
-    for (int u = 0; u < UQ; ++u) {
-      const int r = 4 * (q0 + u * AWARPS) + t;
-      if (4 * (q0 + u * AWARPS) < nrows) {  // warp-uniform
-        double a[4];
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt) a[mt] = r < nrows ? Vs[r * AVP + 8 * mt + g] : 0.0;
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-          for (int nt = 0; nt < QNC / 8; ++nt) dmma884(acc[mt][nt], a[mt], b[u][nt]);
+    for (int nt = 0; nt < 2; ++nt) {
+      const double s0 = (acc[0][nt][0] + acc[1][nt][0]) + (acc[2][nt][0] + acc[3][nt][0]);
+      const double s1 = (acc[0][nt][1] + acc[1][nt][1]) + (acc[2][nt][1] + acc[3][nt][1]);
+      const int e = (8 * mt + g) * QNC + 16 * nh + 8 * nt + 2 * t;
+      if (CR == 1) {
+        Wex[e] = s0;
+        Wex[e + 1] = s1;
+      } else {
+        for (int dst = 0; dst < CR; ++dst) {
+          double* remote = cluster.map_shared_rank(Wex, dst) + cr * WSZ;
+          remote[e] = s0;
+          remote[e + 1] = s1;
+        }
       }
-    }
-  }
-#pragma unroll
-  for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < QNC / 8; ++nt) {
-      Wpart[warp * (QNB * QNC) + (8 * mt + g) * QNC + 8 * nt + 2 * t] = acc[mt][nt][0];
-      Wpart[warp * (QNB * QNC) + (8 * mt + g) * QNC + 8 * nt + 2 * t + 1] = acc[mt][nt][1];
-    }
-  __syncthreads();
-  for (int e = tid; e < QNB * QNC; e += ATHREADS) {
-    double s = 0.0;
-#pragma unroll
-    for (int w = 0; w < AWARPS; ++w) s += Wpart[w * (QNB * QNC) + e];
-    if (CR == 1) {
-      Wex[e] = s;
-    } else {
-      for (int dst = 0; dst < CR; ++dst) cluster.map_shared_rank(Wex, dst)[cr * (QNB * QNC) + e] = s;
     }
   }
   if (CR > 1) cluster.sync(); else __syncthreads();
-  for (int e = tid; e < QNB * QNC; e += ATHREADS) {  // total over the CTAs in rank order, kept in Wpart[0..512)
+  for (int e = tid; e < WSZ; e += ATHREADS) {  // total over the CTAs in rank order
     double s = 0.0;
-    for (int src = 0; src < CR; ++src) s += Wex[src * (QNB * QNC) + e];
-    Wpart[e] = s;
+    for (int src = 0; src < CR; ++src) s += Wex[src * WSZ + e];
+    Wtot[e] = s;
   }
   __syncthreads();
-  for (int e = tid; e < QNB * QNC; e += ATHREADS) {
+  for (int e = tid; e < WSZ; e += ATHREADS) {
     const int i = e / QNC, cc = e % QNC;
     double s = 0.0;
     if (transT) {
-      for (int k = 0; k <= i; ++k) s += Tsm[k * QNB + i] * Wpart[k * QNC + cc];
+      for (int k = 0; k <= i; ++k) s += Tsm[k * QNB + i] * Wtot[k * QNC + cc];
     } else {
-      for (int k = i; k < QNB; ++k) s += Tsm[i * QNB + k] * Wpart[k * QNC + cc];
+      for (int k = i; k < QNB; ++k) s += Tsm[i * QNB + k] * Wtot[k * QNC + cc];
     }
     W2[e] = -s;
   }
   __syncthreads();
-  // ---- phase 2: C += V W2 on this CTA's rows (M = rows, N = 16, K = 32; warps take groups of 8 rows) ----
+  // ---- phase 2: C += V W2 on this CTA's rows (M = rows, N = 32, K = 32; warps take groups of 8 rows) ----
   const int n_oct = (nrows + 7) / 8;
-  constexpr int UO = 4;  // row groups per batch
+  constexpr int UO = 2;  // row groups per batch
   for (int o0 = warp; o0 < n_oct; o0 += UO * AWARPS) {
     double cacc[UO][QNC / 8][2];
 #pragma unroll
@@ -328,7 +337,7 @@ __global__ void __launch_bounds__(ATHREADS, 1) qr_apply_kernel(const double* __r
 #pragma unroll
       for (int u = 0; u < UO; ++u) {
         const int r = 8 * (o0 + u * AWARPS) + g;
-        const double a = r < nrows ? Vs[r * AVP + 4 * ks + t] : 0.0;
+        const double a = vp > 0 ? (r < nrows ? Vs[r * vp + 4 * ks + t] : 0.0) : vglobal(r, 4 * ks + t);
 #pragma unroll
         for (int nt = 0; nt < QNC / 8; ++nt) dmma884(cacc[u][nt], a, bw[nt]);
       }
@@ -429,8 +438,11 @@ static int launch_apply(const double* Wv, int ldv, int m, int j0, int nbp, const
   int CR = 1;
   while (CR < QMAXC && (rows + CR - 1) / CR > 256) CR *= 2;
   const int RB = ((rows + CR - 1) / CR + 7) / 8 * 8;
-  const size_t smem = sizeof(double) * ((size_t)QNB * QNB + (size_t)AWARPS * QNB * QNC + (size_t)QMAXC * QNB * QNC + (size_t)QNB * QNC + (size_t)RB * AVP);
-  TN_REQUIRE(smem <= 227 * 1024, "tn_qr: %d rows exceed the apply capacity", rows);
+  const size_t fixed = sizeof(double) * ((size_t)QNB * QNB + (size_t)QMAXC * QNB * QNC + 2 * (size_t)QNB * QNC);
+  int vp = AVP;
+  if (fixed + sizeof(double) * (size_t)RB * vp > 227 * 1024) vp = QNB;
+  if (fixed + sizeof(double) * (size_t)RB * vp > 227 * 1024) vp = 0;   // too tall to stage: reflectors are read from global / L2
+  const size_t smem = fixed + sizeof(double) * (size_t)RB * vp;
   static size_t configured = 0;
   if (smem > configured) {
     TN_CUDA(cudaFuncSetAttribute(qr_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -448,7 +460,7 @@ static int launch_apply(const double* Wv, int ldv, int m, int j0, int nbp, const
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  TN_CUDA(cudaLaunchKernelEx(&cfg, qr_apply_kernel, Wv, ldv, m, j0, nbp, T, transT, Cm, ldc, c_begin, c_end, RB));
+  TN_CUDA(cudaLaunchKernelEx(&cfg, qr_apply_kernel, Wv, ldv, m, j0, nbp, T, transT, Cm, ldc, c_begin, c_end, RB, vp));
   TN_LAUNCHED();
   return TN_OK;
 }
