@@ -20,6 +20,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -391,6 +392,20 @@ __global__ void qr_eye_kernel(double* __restrict__ Q, int m, int k) {
     Q[i] = (i / k == i % k) ? 1.0 : 0.0;
 }
 
+struct QrSide {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static QrSide* qr_side() {
+  static QrSide x;
+  if (!x.s) {
+    if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return &x;
+}
+
 static int grid_for(long long n) { return (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8); }
 
 template <int RPT, bool KEEP>
@@ -499,10 +514,27 @@ extern "C" int tn_qr_householder(const double* A, int m, int n, int trans_in, do
   // work copy of A (row-major m x n)
   qr_copy_kernel<<<dim3((n + 31) / 32, (m + 31) / 32), tb, 0, stream>>>(A, trans_in ? m : n, W, n, m, n, trans_in ? 1 : 0);
   TN_LAUNCHED();
+  // right-looking with look-ahead: after panel p, its reflectors are applied to the columns of panel p+1 first; the update of the
+  // remaining columns then runs on a side stream while panel p+1 (latency bound, a handful of SMs) is factored on the main stream
+  QrSide* side = (panels > 2 && n > 4 * QNB && !getenv("TNALG_QR_NO_LOOKAHEAD")) ? qr_side() : nullptr;
   for (int p = 0; p < panels; ++p) {
     const int j0 = p * QNB, nbp = std::min(QNB, k - j0);
+    const double* Tp = Tall + (size_t)p * QNB * QNB;
     TN_CHECK(launch_panel(W, n, m, j0, nbp, tau, Tall + (size_t)p * QNB * QNB, stream));
-    TN_CHECK(launch_apply(W, n, m, j0, nbp, Tall + (size_t)p * QNB * QNB, 1, W, n, j0 + nbp, n, stream));
+    const int next_end = std::min(n, j0 + nbp + QNB);
+    if (!side || next_end >= n) {
+      if (side && p > 0) TN_CUDA(cudaStreamWaitEvent(stream, side->join, 0));
+      TN_CHECK(launch_apply(W, n, m, j0, nbp, Tp, 1, W, n, j0 + nbp, n, stream));
+      if (side) side = nullptr;   // tail: plain ordering from here on
+      continue;
+    }
+    if (p > 0) TN_CUDA(cudaStreamWaitEvent(stream, side->join, 0));   // the previous wide update has reached these columns
+    TN_CHECK(launch_apply(W, n, m, j0, nbp, Tp, 1, W, n, j0 + nbp, next_end, stream));
+    TN_CUDA(cudaEventRecord(side->fork, stream));
+    TN_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
+    TN_CHECK(launch_apply(W, n, m, j0, nbp, Tp, 1, W, n, next_end, n, side->s));
+    TN_CUDA(cudaEventRecord(side->join, side->s));
+    if (p == panels - 1) TN_CUDA(cudaStreamWaitEvent(stream, side->join, 0));   // wide matrix: the last update still runs on the side stream
   }
   qr_extract_r_kernel<<<grid_for((long long)k * n), 256, 0, stream>>>(W, n, R, k, n);
   TN_LAUNCHED();
