@@ -368,6 +368,55 @@ def run_sweeps(torch, dist, A, para, steps, world, dev):
                 max_over_ranks=max_over_ranks)
 
 
+def _debug_sweep(torch, A, para):
+    """one sweep with finite-value checks after every primitive (debugging aid, TN_BENCH_DEBUG=1)"""
+    from tnalg_b200 import ops
+    from tnalg_b200.DMRG_anyH import sweep_order
+    be = ops.backend()
+    fin = lambda t: bool(torch.isfinite(t).all())  # noqa: E731
+    qr_real, env_real, lz_real, mp_real = be.qr_tensor, be.env_update, be.lanczos, be.mode_product
+
+    def qr_chk(T, l2r):
+        Q, R = qr_real(T, l2r)
+        torch.cuda.synchronize()
+        if not (fin(Q) and fin(R)):
+            Q2, R2 = qr_real(T, l2r)
+            raise RuntimeError('QR non-finite: T %s finite=%s l2r=%s |T|max=%g; repeat finite=%s ptr=%x'
+                               % (tuple(T.shape), fin(T), l2r, float(T.abs().max()), fin(Q2) and fin(R2), T.data_ptr()))
+        return Q, R
+
+    def mp_chk(T, mat, bond):
+        out = mp_real(T, mat, bond)
+        if not fin(out):
+            raise RuntimeError('mode_product non-finite: T %s %s mat %s %s bond %d' % (tuple(T.shape), fin(T), tuple(mat.shape), fin(mat), bond))
+        return out
+
+    def env_chk(direction, T, outputs):
+        res = env_real(direction, T, outputs)
+        for r in res:
+            if not fin(r):
+                raise RuntimeError('env_update non-finite: T %s finite=%s inputs finite=%s' % (tuple(T.shape), fin(T), [[E is None or fin(E) for E, _ in ln] for ln in outputs]))
+        return res
+
+    def lz_chk(plan, tau, v0, tol, **kw):
+        if not fin(v0):
+            raise RuntimeError('Lanczos start vector non-finite %s' % (plan.shape,))
+        y = plan.matvec(v0.reshape(plan.shape))
+        if not fin(y):
+            raise RuntimeError('matvec non-finite %s' % (plan.shape,))
+        return lz_real(plan, tau, v0, tol, **kw)
+    be.qr_tensor, be.env_update, be.lanczos, be.mode_product = qr_chk, env_chk, lz_chk, mp_chk
+    try:
+        for n in sweep_order(para['l'], para['ob_position']):
+            try:
+                A.update_tensor_eigs(n, para['index1'], para['index2'], para['coeff1'], para['coeff2'], para['tau'], para['is_real'], tol=para['eigs_tol'])
+            except Exception as e:
+                print('DEBUG: failed at site %d: %s' % (n, e), file=sys.stderr, flush=True)
+                raise
+    finally:
+        be.qr_tensor, be.env_update, be.lanczos, be.mode_product = qr_real, env_real, lz_real, mp_real
+
+
 def quick_workload(torch, dist, name, world, dev, warmup=1, steps=1):
     """a short run of another BASELINE configuration (sweep wall-time, matvecs/s) for the `other_workloads` block"""
     from tnalg_b200.DMRG_anyH import sweep_once
@@ -377,6 +426,8 @@ def quick_workload(torch, dist, name, world, dev, warmup=1, steps=1):
     A = MpsOpenBoundaryClass(para['l'], para['d'], para['chi'], operators=para['op'], is_save_op=True, eig_way=1)
     A.sync_replicas()
     A.correct_orthogonal_center(para['ob_position'])
+    if os.environ.get('TN_BENCH_DEBUG'):
+        _debug_sweep(torch, A, para)
     for _ in range(warmup):
         sweep_once(A, para)
     r = run_sweeps(torch, dist, A, para, steps, world, dev)
@@ -500,7 +551,7 @@ def run_ours(args, para, workload):
             traffic = None
 
     other = {}
-    if not args.no_other and workload == 'j1j2_6x6_chi1024':
+    if not args.no_other and args.workload == 'j1j2_6x6_chi1024':
         del x, y
         torch.cuda.empty_cache()
         if world == 1:

@@ -391,3 +391,29 @@ def test_library_collectives_on_two_gpus():
            '--master-port', '29517', os.path.join(root, 'tests', 'multigpu_check.py')]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and 'multigpu_check ok' in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_huge_norms_do_not_overflow(be):
+    """un-normalised random MPS tensors of a long chain reach norms of 1e300 (a factor sqrt(d*chi) per site of the initial gauge
+    pass); the reference survives because LAPACK/ARPACK norms are scaled -- QR and the Lanczos start vector must as well"""
+    rng = np.random.RandomState(0)
+    a = rng.randn(300, 120) * 1e298
+    Q, R = be.qr(be.from_numpy(a))
+    q, r = be.to_numpy(Q), be.to_numpy(R)
+    assert np.isfinite(q).all() and np.isfinite(r).all()
+    assert np.abs(q.T @ q - np.eye(120)).max() < 1e-13 and np.abs(q @ (r / 1e298) - a / 1e298).max() < 1e-12
+    tiny = rng.randn(64, 64) * 1e-300
+    Q, R = be.qr(be.from_numpy(tiny))
+    q, r = be.to_numpy(Q), be.to_numpy(R)
+    assert np.abs(q.T @ q - np.eye(64)).max() < 1e-13 and np.abs(q @ (r * 1e300) - tiny * 1e300).max() < 1e-12
+    from tnalg_b200 import Parameters as Pm
+    from tnalg_b200.MPSClass import MpsOpenBoundaryClass
+    para = Pm.generate_parameters_dmrg('chain')
+    para.update(l=6, chi=8)
+    para = Pm.make_consistent_parameter_dmrg(para)
+    np.random.seed(0)
+    A = MpsOpenBoundaryClass(para['l'], para['d'], para['chi'], operators=para['op'], is_save_op=True, eig_way=1)
+    A.correct_orthogonal_center(2)
+    A.mps[2] = A.mps[2] * 1e299
+    A.update_tensor_eigs(2, para['index1'], para['index2'], para['coeff1'], para['coeff2'], para['tau'], True, tol=1e-10)
+    assert A.last_eig['converged'] and abs(A.norm_mps() - 1) < 1e-12

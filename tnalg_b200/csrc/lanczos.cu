@@ -34,6 +34,8 @@ struct LanczosState {
   double lock_h[kMaxNcv]; // coefficients against locked (deflated) vectors, tn_lanczos_generic
   double u[kMaxNcv];      // Ritz vector in the Krylov basis
   double nrm2, inv_beta;
+  double scale2[2];              // power-of-two pre-scaling of the start vector (its square must not overflow)
+  unsigned long long scale_slot;
   int need2, pad2;        // DGKS: second Gram-Schmidt pass needed for the current step
   // status record copied to the host once per cycle
   double theta, resid, lambda, s_restart;
@@ -386,6 +388,10 @@ static int lanczos_core(LanczosOp& op, long long n, long long n_loc, long long o
   if (sliced) TN_CUDA(cudaMemsetAsync(V, 0, sizeof(double) * (size_t)ldv * (m + 2), stream));  // the pads travel through all-gathers
   // v_0 = v0 / |v0|
   TN_CUDA(cudaMemcpyAsync(vec(0), v0 + off, sizeof(double) * n_loc, cudaMemcpyDeviceToDevice, stream));
+  // an un-normalised centre tensor of a long random chain can carry a norm of 1e300: scale by a power of two before squaring
+  // (the scale is taken from the full vector, which every rank holds, so sliced ranks agree on it)
+  TN_CHECK(launch_pow2_scale(v0, n, st->scale2, &st->scale_slot, stream));
+  TN_CHECK(launch_scale_dev(vec(0), st->scale2, n_loc, stream));
   TN_CHECK(project_locked(vec(0)));
   TN_CHECK(launch_multidot(vec(0), ldv, 1, vec(0), n_loc, &st->nrm2, partial, counter, stream));
   TN_CHECK(reduce(&st->nrm2, 1));

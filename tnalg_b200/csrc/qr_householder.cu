@@ -23,6 +23,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "vector_ops.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -359,13 +360,14 @@ __global__ void __launch_bounds__(ATHREADS, 1) qr_apply_kernel(const double* __r
 
 // out (rows x cols, ld ldo) = in^T or in;  tiled through shared memory
 __global__ void qr_copy_kernel(const double* __restrict__ in, int ldi, double* __restrict__ out, int ldo, int rows_out, int cols_out,
-                               int transpose) {
+                               int transpose, const double* __restrict__ scale) {
   __shared__ double tile[32][33];
+  const double sc = scale ? *scale : 1.0;  // power of two: exact
   const int bx = blockIdx.x * 32, by = blockIdx.y * 32;  // bx: output column block, by: output row block
   if (!transpose) {
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
       const int r = by + i, c = bx + threadIdx.x;
-      if (r < rows_out && c < cols_out) out[(size_t)r * ldo + c] = in[(size_t)r * ldi + c];
+      if (r < rows_out && c < cols_out) out[(size_t)r * ldo + c] = sc * in[(size_t)r * ldi + c];
     }
     return;
   }
@@ -376,15 +378,16 @@ __global__ void qr_copy_kernel(const double* __restrict__ in, int ldi, double* _
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int r = by + i, c = bx + threadIdx.x;
-    if (r < rows_out && c < cols_out) out[(size_t)r * ldo + c] = tile[threadIdx.x][i];
+    if (r < rows_out && c < cols_out) out[(size_t)r * ldo + c] = sc * tile[threadIdx.x][i];
   }
 }
 
 // R (k x n) = upper trapezoid of the factored work matrix; Q (m x k) = [1; 0]
-__global__ void qr_extract_r_kernel(const double* __restrict__ W, int ld, double* __restrict__ Rm, int k, int n) {
+__global__ void qr_extract_r_kernel(const double* __restrict__ W, int ld, double* __restrict__ Rm, int k, int n, const double* __restrict__ scale) {
+  const double sc = *scale;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)k * n; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / n), c = (int)(i % n);
-    Rm[i] = c >= r ? W[(size_t)r * ld + c] : 0.0;
+    Rm[i] = c >= r ? sc * W[(size_t)r * ld + c] : 0.0;
   }
 }
 __global__ void qr_eye_kernel(double* __restrict__ Q, int m, int k) {
@@ -488,7 +491,7 @@ extern "C" size_t tn_qr_workspace_bytes(int m, int n) {
   const int k = std::min(m, n);
   const size_t panels = (size_t)(k + QNB - 1) / QNB;
   return align_up(sizeof(double) * (size_t)m * n) + align_up(sizeof(double) * (size_t)m * k) + align_up(sizeof(double) * panels * QNB * QNB) +
-         align_up(sizeof(double) * (size_t)(k + QNB)) + 1024;
+         align_up(sizeof(double) * (size_t)(k + QNB)) + 2 * 256 + 1024;
 }
 
 // trans_in != 0: the input is A^T, stored (n, m) row-major (the right-to-left move factorises the transposed matricisation
@@ -509,10 +512,15 @@ extern "C" int tn_qr_householder(const double* A, int m, int n, int trans_in, do
   double* Qw = cw.take<double>((size_t)m * k);
   double* Tall = cw.take<double>((size_t)panels * QNB * QNB);
   double* tau = cw.take<double>((size_t)(k + QNB));
-  TN_REQUIRE(W && Qw && Tall && tau, "tn_qr_householder: workspace carve failed");
+  double* scale2 = cw.take<double>(2);
+  unsigned long long* slot = cw.take<unsigned long long>(1);
+  TN_REQUIRE(W && Qw && Tall && tau && scale2 && slot, "tn_qr_householder: workspace carve failed");
   const dim3 tb(32, 8);
-  // work copy of A (row-major m x n)
-  qr_copy_kernel<<<dim3((n + 31) / 32, (m + 31) / 32), tb, 0, stream>>>(A, trans_in ? m : n, W, n, m, n, trans_in ? 1 : 0);
+  // The column norms are formed as plain sums of squares, so the work copy is A scaled by a power of two to max|a_ij| in [1/2, 1)
+  // (exact; R is scaled back): un-normalised MPS tensors reach 1e300 on long chains and their squares would overflow
+  TN_CUDA(cudaMemsetAsync(slot, 0, sizeof(unsigned long long), stream));
+  TN_CHECK(launch_pow2_scale(A, (long long)m * n, scale2, slot, stream));
+  qr_copy_kernel<<<dim3((n + 31) / 32, (m + 31) / 32), tb, 0, stream>>>(A, trans_in ? m : n, W, n, m, n, trans_in ? 1 : 0, scale2);
   TN_LAUNCHED();
   // right-looking with look-ahead: after panel p, its reflectors are applied to the columns of panel p+1 first; the update of the
   // remaining columns then runs on a side stream while panel p+1 (latency bound, a handful of SMs) is factored on the main stream
@@ -536,7 +544,7 @@ extern "C" int tn_qr_householder(const double* A, int m, int n, int trans_in, do
     TN_CUDA(cudaEventRecord(side->join, side->s));
     if (p == panels - 1) TN_CUDA(cudaStreamWaitEvent(stream, side->join, 0));   // wide matrix: the last update still runs on the side stream
   }
-  qr_extract_r_kernel<<<grid_for((long long)k * n), 256, 0, stream>>>(W, n, R, k, n);
+  qr_extract_r_kernel<<<grid_for((long long)k * n), 256, 0, stream>>>(W, n, R, k, n, scale2 + 1);
   TN_LAUNCHED();
   double* Qdst = trans_q ? Qw : Q;
   qr_eye_kernel<<<grid_for((long long)m * k), 256, 0, stream>>>(Qdst, m, k);
@@ -546,7 +554,7 @@ extern "C" int tn_qr_householder(const double* A, int m, int n, int trans_in, do
     TN_CHECK(launch_apply(W, n, m, j0, nbp, Tall + (size_t)p * QNB * QNB, 0, Qdst, k, j0, k, stream));
   }
   if (trans_q) {
-    qr_copy_kernel<<<dim3((m + 31) / 32, (k + 31) / 32), tb, 0, stream>>>(Qw, k, Q, m, k, m, 1);
+    qr_copy_kernel<<<dim3((m + 31) / 32, (k + 31) / 32), tb, 0, stream>>>(Qw, k, Q, m, k, m, 1, nullptr);
     TN_LAUNCHED();
   }
   return TN_OK;

@@ -183,6 +183,32 @@ int launch_scale_dev(double* x, const double* scale, long long n, cudaStream_t s
   return TN_OK;
 }
 
+__global__ void maxabs_kernel(const double* __restrict__ x, long long n, unsigned long long* slot) {
+  double m = 0.0;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) m = fmax(m, fabs(x[e]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  // non-negative doubles order like their bit patterns (NaN never wins fmax; Inf is the largest pattern)
+  if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(slot, (unsigned long long)__double_as_longlong(m));
+}
+__global__ void pow2_scale_kernel(unsigned long long* slot, double* scale2) {
+  const double m = __longlong_as_double((long long)*slot);
+  *slot = 0ull;
+  int e = 0;
+  if (m > 0.0 && m < 1.7e308) frexp(m, &e);
+  scale2[0] = ldexp(1.0, -e);
+  scale2[1] = ldexp(1.0, e);
+}
+
+int launch_pow2_scale(const double* x, long long n, double* scale2, unsigned long long* slot, cudaStream_t stream) {
+  int grid = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8);
+  maxabs_kernel<<<grid, 256, 0, stream>>>(x, n, slot);
+  TN_LAUNCHED();
+  pow2_scale_kernel<<<1, 1, 0, stream>>>(slot, scale2);
+  TN_LAUNCHED();
+  return TN_OK;
+}
+
 __global__ void trace_kernel(const double* __restrict__ E, int n, double* result) {
   double acc = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) acc += E[(long long)i * n + i];

@@ -24,6 +24,9 @@ int launch_multi_axpy(double* w, const double* V, long long ldv, int nvec, const
                       const int* skip_flag = nullptr);
 // y[e] = sum_i u[i] * V[i*ldv + e]
 int launch_combine(double* y, const double* V, long long ldv, int nvec, const double* u, long long n, cudaStream_t stream);
+// overflow-safe scaling: scale2[0] = 2^-e, scale2[1] = 2^e with 2^(e-1) <= max|x| < 2^e (both 1 for a zero or non-finite x).
+// slot: one zero-initialised unsigned long long of scratch (the kernel leaves it zero again).  Exact, order independent.
+int launch_pow2_scale(const double* x, long long n, double* scale2, unsigned long long* slot, cudaStream_t stream);
 // x[e] *= *scale (device scalar)
 int launch_scale_dev(double* x, const double* scale, long long n, cudaStream_t stream);
 
