@@ -160,20 +160,25 @@ def mode_product(tensor, mat, bond):
 def transfer_l2r(tensor, op=None, env=None):
     """E'[b,b'] = sum conj(T[a,s,b]) E[a,a'] op[s,s'] T[a',s',b']
     (bound_vec_operator_left2right, TensorBasicModule.py:530-573; env/op None = identity)."""
-    ket = tensor if op is None else np.einsum('st,atb->asb', op, tensor)
+    a, d, b = tensor.shape
+    # the same three matrix products as the reference (:554-568): op on the physical bond, v . T, T^H . (v T)
+    ket = tensor if op is None else np.moveaxis(np.tensordot(np.asarray(op), tensor, axes=([1], [1])), 0, 1)
+    ket = np.ascontiguousarray(ket)
     if env is not None:
-        ket = np.einsum('xa,asb->xsb', env, ket)
-    return np.einsum('asb,asc->bc', tensor.conj(), ket)
+        ket = env.dot(ket.reshape(a, d * b))
+    return tensor.conj().reshape(a * d, b).T.dot(ket.reshape(a * d, b))
 
 
 def transfer_r2l(tensor, op=None, env=None):
     """E'[a,a'] = sum conj(T[a,s,b]) E[b,b'] op[s,s'] T[a',s',b']
     (bound_vec_operator_right2left, TensorBasicModule.py:576-619)."""
-    ket = tensor if op is None else np.einsum('st,atb->asb', op, tensor)
-    bra = tensor.conj()
+    a, d, b = tensor.shape
+    ket = tensor if op is None else np.moveaxis(np.tensordot(np.asarray(op), tensor, axes=([1], [1])), 0, 1)
+    ket = np.ascontiguousarray(ket)
+    bra = tensor.conj().reshape(a * d, b)
     if env is not None:
-        bra = np.einsum('asb,bc->asc', bra, env)
-    return np.einsum('asc,xsc->ax', bra, ket)
+        bra = bra.dot(env)
+    return bra.reshape(a, d * b).dot(ket.reshape(a, d * b).T)
 
 
 def decompose_l2r(tensor, way='qr'):
