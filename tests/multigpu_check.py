@@ -37,6 +37,7 @@ def main():
     comm.broadcast_many(bufs, [j % world for j in range(5)])
     for j in range(5):
         assert float(bufs[j][3, 3]) == (j % world) * 10 + j
+    be.shard_min_rows, be.shard_min_n = 4, 256      # slice even small sites in this check
     # ---- local problem: 4x3 lattice, chi = 96 ----
     para = Pm.generate_parameters_dmrg('square')
     para.update(square_width=4, square_height=3, chi=96, op=para['op'][:6], eigs_tol=1e-10)

@@ -31,8 +31,6 @@ namespace tn {
 
 namespace {
 constexpr int QNB = 32;        // panel width
-constexpr int QTHREADS = 512;  // panel kernel: 16 warps
-constexpr int QWARPS = QTHREADS / 32;
 constexpr int QMAXC = 8;       // portable cluster size
 constexpr int QSLOT = 2 * QNB; // doubles one CTA contributes per column: g[32], row j[32]
 constexpr int QMAX_RPT = 48;   // rows per thread of the panel kernel -> 768 rows per CTA, 6144 per cluster
@@ -57,28 +55,29 @@ __device__ __forceinline__ double warp_sum_q(double v) {
 // column-j broadcast is a warp shuffle and the rank-1 update touches registers only; shared memory carries just the
 // cross-warp / cross-CTA partial sums (double-buffered by the parity of j: ONE CTA barrier -- plus one cluster barrier when
 // the panel spans several CTAs -- per column).
-template <int RPT, bool KEEP>
-__global__ void __launch_bounds__(QTHREADS, 1) qr_panel_kernel(double* __restrict__ W, int ld, int m, int j0, int nbp,
+template <int RPT, bool KEEP, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) qr_panel_kernel(double* __restrict__ W, int ld, int m, int j0, int nbp,
                                                                double* __restrict__ tau_out, double* __restrict__ T_out) {
   cg::cluster_group cluster = cg::this_cluster();
   const int C = (int)cluster.num_blocks(), c = (int)cluster.block_rank();
-  __shared__ double red[2][QWARPS][QNB];        // per-warp partial Gram rows
+  __shared__ double red[2][WARPS][QNB];        // per-warp partial Gram rows
   __shared__ double rowj[2][QNB];               // row j of the panel (CTA 0)
   __shared__ double slots[2][QMAXC][QSLOT];     // cluster exchange: [parity][source CTA][g(32) | row j(32)]
   __shared__ double Z[QNB * QNB];               // Z[k*32 + j] = V_k^T v_j (k < j)
   __shared__ double Ts[QNB * QNB];              // compact-WY factor
   __shared__ double taus[QNB];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int DI = (QNB / WARPS) < RPT ? (QNB / WARPS) : RPT;  // slots that may hold rows of the diagonal block (panel rows < 32)
   const int rows_total = m - j0;
-  const int row_lo = c * (RPT * QWARPS);        // first panel row of this CTA
+  const int row_lo = c * (RPT * WARPS);        // first panel row of this CTA
 
   double x[RPT];
 #pragma unroll
   for (int i = 0; i < RPT; ++i) {
-    const int pr = row_lo + i * QWARPS + warp;  // panel row
+    const int pr = row_lo + i * WARPS + warp;  // panel row
     x[i] = (pr < rows_total && lane < nbp) ? W[(size_t)(j0 + pr) * ld + j0 + lane] : 0.0;
   }
-  for (int idx = tid; idx < QNB * QNB; idx += QTHREADS) {
+  for (int idx = tid; idx < QNB * QNB; idx += (WARPS * 32)) {
     Z[idx] = 0.0;
     Ts[idx] = 0.0;
   }
@@ -89,7 +88,7 @@ __global__ void __launch_bounds__(QTHREADS, 1) qr_panel_kernel(double* __restric
   for (int j = 0; j < nbp; ++j) {
     const int par = j & 1;
     // ---- row j of the panel Gram matrix, g_k = sum_{rows >= j} P[r,j] P[r,k], over this thread's rows ----
-    // only the rows of the diagonal block (panel rows < 32: i < 2 of CTA 0) can lie above row j; all others take the plain FMA
+    // only the rows of the diagonal block (panel rows < 32: slots i < DI of CTA 0) can lie above row j; all others take the plain FMA
     double xjs[KEEP ? RPT : 1];  // column j of this thread's rows (one warp shuffle per row; reused by the update when KEEP)
     {
       double acc0 = 0.0, acc1 = 0.0;
@@ -98,17 +97,22 @@ __global__ void __launch_bounds__(QTHREADS, 1) qr_panel_kernel(double* __restric
         const double xj = __shfl_sync(0xffffffffu, x[i], j);
         if (KEEP) xjs[i] = xj;
         double xi = x[i];
-        if (i < 2) xi = (row_lo + i * QWARPS + warp >= j) ? xi : 0.0;
+        if (i < DI) xi = (row_lo + i * WARPS + warp >= j) ? xi : 0.0;
         if (i & 1) acc1 = fma(xj, xi, acc1); else acc0 = fma(xj, xi, acc0);
       }
       red[par][warp][lane] = acc0 + acc1;
-      if (c == 0 && warp == (j & (QWARPS - 1))) rowj[par][lane] = (RPT > 1 && j >= QWARPS) ? x[RPT > 1 ? 1 : 0] : x[0];  // row j = i*16 + warp
+      if (c == 0 && warp == (j & (WARPS - 1))) {  // row j of the panel = slot i = j / WARPS of this warp
+        double v = 0.0;
+#pragma unroll
+        for (int i = 0; i < DI; ++i) v = (i * WARPS + warp == j) ? x[i] : v;
+        rowj[par][lane] = v;
+      }
     }
     __syncthreads();
     double gk = 0.0, gj = 0.0, rjk, alpha;
     if (C == 1) {
 #pragma unroll
-      for (int w = 0; w < QWARPS; ++w) {
+      for (int w = 0; w < WARPS; ++w) {
         gk += red[par][w][lane];
         gj += red[par][w][j];
       }
@@ -118,7 +122,7 @@ __global__ void __launch_bounds__(QTHREADS, 1) qr_panel_kernel(double* __restric
       if (warp == 0) {
         double g = 0.0;
 #pragma unroll
-        for (int w = 0; w < QWARPS; ++w) g += red[par][w][lane];
+        for (int w = 0; w < WARPS; ++w) g += red[par][w][lane];
         const double rj = (c == 0) ? rowj[par][lane] : 0.0;
         for (int dst = 0; dst < C; ++dst) {
           double* remote = cluster.map_shared_rank(&slots[0][0][0], dst);
@@ -161,8 +165,8 @@ __global__ void __launch_bounds__(QTHREADS, 1) qr_panel_kernel(double* __restric
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
       const double xj = KEEP ? xjs[i] : __shfl_sync(0xffffffffu, x[i], j);
-      if (i < 2) {
-        const int pr = row_lo + i * QWARPS + warp;
+      if (i < DI) {
+        const int pr = row_lo + i * WARPS + warp;
         if (pr > j) {
           x[i] = fma(-coef, xj, x[i]);
           if (lane == j) x[i] = xj * scale;
@@ -175,7 +179,7 @@ __global__ void __launch_bounds__(QTHREADS, 1) qr_panel_kernel(double* __restric
         if (lane == j) x[i] = xj * scale;
       }
     }
-    if (c == 0 && warp == (j & (QWARPS - 1))) {  // the warp that owns row j records the T-factor inputs
+    if (c == 0 && warp == (j & (WARPS - 1))) {  // the warp that owns row j records the T-factor inputs
       if (lane < j) Z[lane * QNB + j] = y;
       if (lane == j) taus[j] = tau;
     }
@@ -186,7 +190,7 @@ __global__ void __launch_bounds__(QTHREADS, 1) qr_panel_kernel(double* __restric
   if (c == 0) {
     for (int j = 0; j < nbp; ++j) {
       const double tj = taus[j];
-      for (int i = warp; i < j; i += QWARPS) {
+      for (int i = warp; i < j; i += WARPS) {
         double s = (lane >= i && lane < j) ? Ts[i * QNB + lane] * Z[lane * QNB + j] : 0.0;
         s = warp_sum_q(s);
         if (lane == 0) Ts[i * QNB + j] = -tj * s;
@@ -194,35 +198,40 @@ __global__ void __launch_bounds__(QTHREADS, 1) qr_panel_kernel(double* __restric
       if (tid == 0) Ts[j * QNB + j] = tj;
       __syncthreads();
     }
-    for (int idx = tid; idx < QNB * QNB; idx += QTHREADS) T_out[idx] = Ts[idx];
+    for (int idx = tid; idx < QNB * QNB; idx += (WARPS * 32)) T_out[idx] = Ts[idx];
     if (tid < nbp) tau_out[j0 + tid] = taus[tid];
   }
 #pragma unroll
   for (int i = 0; i < RPT; ++i) {
-    const int pr = row_lo + i * QWARPS + warp;
+    const int pr = row_lo + i * WARPS + warp;
     if (pr < rows_total && lane < nbp) W[(size_t)(j0 + pr) * ld + j0 + lane] = x[i];
   }
   if (C > 1) cluster.sync();  // no CTA exits while a peer may still address its shared memory
 }
 
 // Cm[j0:m, c_begin:c_end] <- (1 - V op(T) V^T) Cm[j0:m, c_begin:c_end];  transT != 0: op(T) = T^T.
-// One cluster per strip of QNC = 32 columns; the CTAs of the cluster split the rows (RB each).  The unit-lower-trapezoidal
-// reflector block of the CTA's rows is staged once in shared memory and serves both GEMMs.  Phase 1 (W = V^T C): warp w owns
-// the 8 x 16 output tile (reflectors 8*(w%4).., columns 16*(w/4)..) over all rows of the CTA -- no cross-warp reduction; the
-// CTAs' partial tiles meet through distributed shared memory and are summed in CTA order (deterministic).  Phase 2: C -= V W.
+// One cluster per strip of QNC = 32 columns; the CTAs of the cluster split the rows (RB each).  The kernel is a chain of
+// latencies (it moves ~100 KB and does ~1 MFLOP per CTA), so every global access is made once and in one deep batch: the
+// unit-lower-trapezoidal reflector rows AND the CTA's block of C are staged in shared memory by 32 independent loads per
+// thread, both GEMMs then run from shared memory and the result goes back with plain stores.
+// Phase 1 (W = V^T C): warp w owns the 8 x 16 output tile (reflectors 8*(w%4).., columns 16*(w/4)..) over all rows of the CTA
+// -- no cross-warp reduction; the CTAs' partial tiles meet through distributed shared memory and are summed in CTA order
+// (deterministic).  Phase 2: C -= V (op(T) W).
+// vp / cp: pitches of the staged reflector / C rows (36: conflict-free fragment reads, 32: when the padded blocks would not
+// fit); cp = 0: C is read from global / L2 in both phases; vp = 0: neither block is staged (very tall panels).
 __global__ void __launch_bounds__(ATHREADS, 1) qr_apply_kernel(const double* __restrict__ Wv, int ldv, int m, int j0, int nbp,
                                                                const double* __restrict__ T, int transT, double* __restrict__ Cm,
-                                                               int ldc, int c_begin, int c_end, int RB, int vp) {
-  // vp: pitch of the staged reflector rows (36 conflict-free, 32 when the padded block would not fit); 0: not staged, read from global
+                                                               int ldc, int c_begin, int c_end, int RB, int vp, int cp) {
   cg::cluster_group cluster = cg::this_cluster();
   const int CR = (int)cluster.num_blocks(), cr = (int)cluster.block_rank();
   extern __shared__ __align__(16) double sm_apply[];
   constexpr int WSZ = QNB * QNC;                            // 32 x 32 block of V^T C
   double* Tsm = sm_apply;                                   // 32 x 32
-  double* Wex = Tsm + QNB * QNB;                            // [QMAXC][WSZ] cluster exchange
-  double* Wtot = Wex + QMAXC * WSZ;                         // WSZ: sum over the CTAs
+  double* Wtot = Tsm + QNB * QNB;                           // WSZ: sum over the CTAs
   double* W2 = Wtot + WSZ;                                  // WSZ: -op(T) V^T C
-  double* Vs = W2 + WSZ;                                    // RB x vp reflector rows of this CTA
+  double* Wex = W2 + WSZ;                                   // [CR][WSZ] cluster exchange
+  double* Vs = Wex + (size_t)CR * WSZ;                      // RB x vp reflector rows of this CTA
+  double* Cs = Vs + (size_t)RB * vp;                        // RB x cp block of C
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int strip = blockIdx.x / CR;
   const int c0 = c_begin + strip * QNC;
@@ -235,21 +244,26 @@ __global__ void __launch_bounds__(ATHREADS, 1) qr_apply_kernel(const double* __r
     if (r >= nrows || k >= nbp || rl < k) return 0.0;
     return rl == k ? 1.0 : Wv[(size_t)(row0 + r) * ldv + j0 + k];
   };
-  // reflector rows of this CTA: batches of 8 independent loads per thread (a plain loop would serialise the L2 latency)
-  for (int base = 0; vp > 0 && base < nrows * QNB; base += 8 * ATHREADS) {
-    double v[8];
+  auto cglobal = [&](int r, int cc) -> double { return (r < nrows && cc < c_end) ? Cm[(size_t)(row0 + r) * ldc + cc] : 0.0; };
+  // staging: element idx = r*32 + k of both blocks; 16 + 16 independent loads per thread and pass
+  for (int base = 0; vp > 0 && base < nrows * QNB; base += 16 * ATHREADS) {
+    double v[16], cv[16];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < 16; ++u) {
       const int idx = base + u * ATHREADS + tid;
       const int r = idx >> 5, k = idx & 31;
-      const bool in = idx < nrows * QNB && k < nbp && (row0 + r - j0) > k;
-      v[u] = in ? Wv[(size_t)(row0 + r) * ldv + j0 + k] : 0.0;
+      const bool in = idx < nrows * QNB;
+      v[u] = (in && k < nbp && (row0 + r - j0) > k) ? Wv[(size_t)(row0 + r) * ldv + j0 + k] : 0.0;
+      cv[u] = (cp > 0 && in && c0 + k < c_end) ? Cm[(size_t)(row0 + r) * ldc + c0 + k] : 0.0;
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < 16; ++u) {
       const int idx = base + u * ATHREADS + tid;
       const int r = idx >> 5, k = idx & 31;
-      if (idx < nrows * QNB) Vs[r * vp + k] = (k < nbp && (row0 + r - j0) == k) ? 1.0 : v[u];
+      if (idx < nrows * QNB) {
+        Vs[r * vp + k] = (k < nbp && (row0 + r - j0) == k) ? 1.0 : v[u];
+        if (cp > 0) Cs[r * cp + k] = cv[u];
+      }
     }
   }
   if (CR > 1) cluster.sync();  // peers are resident (remote writes below); doubles as the CTA barrier
@@ -271,8 +285,8 @@ __global__ void __launch_bounds__(ATHREADS, 1) qr_apply_kernel(const double* __r
         const int r = 4 * (q0 + u) + t;  // local row
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
-          const int cc = c0 + 16 * nh + 8 * nt + g;
-          b[u][nt] = (r < nrows && cc < c_end) ? Cm[(size_t)(row0 + r) * ldc + cc] : 0.0;
+          const int kc = 16 * nh + 8 * nt + g;
+          b[u][nt] = cp > 0 ? (r < nrows ? Cs[r * cp + kc] : 0.0) : cglobal(r, c0 + kc);
         }
         a[u] = vp > 0 ? (r < nrows ? Vs[r * vp + 8 * mt + g] : 0.0) : vglobal(r, 8 * mt + g);
       }
@@ -326,9 +340,14 @@ __global__ void __launch_bounds__(ATHREADS, 1) qr_apply_kernel(const double* __r
       const int r = 8 * (o0 + u * AWARPS) + g;
 #pragma unroll
       for (int nt = 0; nt < QNC / 8; ++nt) {
-        const int cc = c0 + 8 * nt + 2 * t;
-        cacc[u][nt][0] = (r < nrows && cc < c_end) ? Cm[(size_t)(row0 + r) * ldc + cc] : 0.0;
-        cacc[u][nt][1] = (r < nrows && cc + 1 < c_end) ? Cm[(size_t)(row0 + r) * ldc + cc + 1] : 0.0;
+        const int kc = 8 * nt + 2 * t;
+        if (cp > 0) {
+          cacc[u][nt][0] = r < nrows ? Cs[r * cp + kc] : 0.0;
+          cacc[u][nt][1] = r < nrows ? Cs[r * cp + kc + 1] : 0.0;
+        } else {
+          cacc[u][nt][0] = cglobal(r, c0 + kc);
+          cacc[u][nt][1] = cglobal(r, c0 + kc + 1);
+        }
       }
     }
 #pragma unroll
@@ -411,11 +430,11 @@ static QrSide* qr_side() {
 
 static int grid_for(long long n) { return (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8); }
 
-template <int RPT, bool KEEP>
+template <int RPT, bool KEEP, int WARPS>
 static int launch_panel_t(double* W, int ld, int m, int j0, int nbp, double* tau, double* T, int C, cudaStream_t stream) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(C);
-  cfg.blockDim = dim3(QTHREADS);
+  cfg.blockDim = dim3(WARPS * 32);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -425,27 +444,31 @@ static int launch_panel_t(double* W, int ld, int m, int j0, int nbp, double* tau
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  TN_CUDA(cudaLaunchKernelEx(&cfg, qr_panel_kernel<RPT, KEEP>, W, ld, m, j0, nbp, tau, T));
+  TN_CUDA(cudaLaunchKernelEx(&cfg, qr_panel_kernel<RPT, KEEP, WARPS>, W, ld, m, j0, nbp, tau, T));
   TN_LAUNCHED();
   return TN_OK;
 }
 
 static int launch_panel(double* W, int ld, int m, int j0, int nbp, double* tau, double* T, cudaStream_t stream) {
   const int rows = m - j0;
-  // 256 rows per CTA (16 per thread: the column-j broadcast of a row costs one shuffle per column) while a cluster of up to 8
-  // CTAs covers the panel; taller panels put more rows into each thread (up to 768 per CTA, 6144 per cluster)
+  // Up to 2048 rows: 8 warps per CTA, 256 rows per CTA (32 per thread, the column-j broadcasts of phase A kept for the update),
+  // a cluster of 1 / 2 / 4 / 8 CTAs.  The per-column cost is instruction issue: few warps keep the redundant scalar work small.
+  // Taller panels: 16 warps, up to 768 rows per CTA (6144 per cluster).
   int C = 1;
   while (C < QMAXC && (rows + C - 1) / C > 256 && rows / (2 * C) >= QNB) C *= 2;
   const int per_cta = (rows + C - 1) / C;
-  const int rpt = (per_cta + QWARPS - 1) / QWARPS;
-  TN_REQUIRE(rpt <= QMAX_RPT, "tn_qr: %d rows exceed the panel capacity (%d rows)", rows, QMAXC * QMAX_RPT * QWARPS);
   TN_REQUIRE(C == 1 || per_cta >= QNB, "tn_qr: internal panel split");
-  if (rpt <= 2) return launch_panel_t<2, true>(W, ld, m, j0, nbp, tau, T, C, stream);
-  if (rpt <= 4) return launch_panel_t<4, true>(W, ld, m, j0, nbp, tau, T, C, stream);
-  if (rpt <= 8) return launch_panel_t<8, true>(W, ld, m, j0, nbp, tau, T, C, stream);
-  if (rpt <= 16) return launch_panel_t<16, true>(W, ld, m, j0, nbp, tau, T, C, stream);
-  if (rpt <= 32) return launch_panel_t<32, false>(W, ld, m, j0, nbp, tau, T, C, stream);
-  return launch_panel_t<QMAX_RPT, false>(W, ld, m, j0, nbp, tau, T, C, stream);
+  if (per_cta <= 256) {
+    const int rpt = (per_cta + 7) / 8;
+    if (rpt <= 4) return launch_panel_t<4, true, 8>(W, ld, m, j0, nbp, tau, T, C, stream);
+    if (rpt <= 8) return launch_panel_t<8, true, 8>(W, ld, m, j0, nbp, tau, T, C, stream);
+    if (rpt <= 16) return launch_panel_t<16, true, 8>(W, ld, m, j0, nbp, tau, T, C, stream);
+    return launch_panel_t<32, true, 8>(W, ld, m, j0, nbp, tau, T, C, stream);
+  }
+  const int rpt = (per_cta + 15) / 16;
+  TN_REQUIRE(rpt <= QMAX_RPT, "tn_qr: %d rows exceed the panel capacity (%d rows)", rows, QMAXC * QMAX_RPT * 16);
+  if (rpt <= 32) return launch_panel_t<32, false, 16>(W, ld, m, j0, nbp, tau, T, C, stream);
+  return launch_panel_t<QMAX_RPT, false, 16>(W, ld, m, j0, nbp, tau, T, C, stream);
 }
 
 static int launch_apply(const double* Wv, int ldv, int m, int j0, int nbp, const double* T, int transT, double* Cm, int ldc,
@@ -456,11 +479,15 @@ static int launch_apply(const double* Wv, int ldv, int m, int j0, int nbp, const
   int CR = 1;
   while (CR < QMAXC && (rows + CR - 1) / CR > 256) CR *= 2;
   const int RB = ((rows + CR - 1) / CR + 7) / 8 * 8;
-  const size_t fixed = sizeof(double) * ((size_t)QNB * QNB + (size_t)QMAXC * QNB * QNC + 2 * (size_t)QNB * QNC);
-  int vp = AVP;
-  if (fixed + sizeof(double) * (size_t)RB * vp > 227 * 1024) vp = QNB;
-  if (fixed + sizeof(double) * (size_t)RB * vp > 227 * 1024) vp = 0;   // too tall to stage: reflectors are read from global / L2
-  const size_t smem = fixed + sizeof(double) * (size_t)RB * vp;
+  const size_t fixed = sizeof(double) * ((size_t)QNB * QNB + (size_t)CR * QNB * QNC + 2 * (size_t)QNB * QNC);
+  const size_t cap = 227 * 1024;
+  auto fits = [&](int v, int c) { return fixed + sizeof(double) * (size_t)RB * (size_t)(v + c) <= cap; };
+  int vp = AVP, cp = AVP;                                 // both blocks staged with padded rows
+  if (!fits(vp, cp)) { vp = QNB; cp = QNB; }              // ... unpadded
+  if (!fits(vp, cp)) { vp = AVP; cp = 0; }                // reflectors only
+  if (!fits(vp, cp)) vp = QNB;
+  if (!fits(vp, cp)) vp = 0;                              // too tall to stage: both operands are read from global / L2
+  const size_t smem = fixed + sizeof(double) * (size_t)RB * (size_t)(vp + cp);
   static size_t configured = 0;
   if (smem > configured) {
     TN_CUDA(cudaFuncSetAttribute(qr_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -478,7 +505,7 @@ static int launch_apply(const double* Wv, int ldv, int m, int j0, int nbp, const
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  TN_CUDA(cudaLaunchKernelEx(&cfg, qr_apply_kernel, Wv, ldv, m, j0, nbp, T, transT, Cm, ldc, c_begin, c_end, RB, vp));
+  TN_CUDA(cudaLaunchKernelEx(&cfg, qr_apply_kernel, Wv, ldv, m, j0, nbp, T, transT, Cm, ldc, c_begin, c_end, RB, vp, cp));
   TN_LAUNCHED();
   return TN_OK;
 }
