@@ -91,16 +91,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) qr_panel_kernel(double* __restr
     // only the rows of the diagonal block (panel rows < 32: slots i < DI of CTA 0) can lie above row j; all others take the plain FMA
     double xjs[KEEP ? RPT : 1];  // column j of this thread's rows (one warp shuffle per row; reused by the update when KEEP)
     {
-      double acc0 = 0.0, acc1 = 0.0;
+      // FP64 results come back after ~38 cycles on this part: 8 independent accumulators and a tree keep the chain short
+      double acc[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] = 0.0;
 #pragma unroll
       for (int i = 0; i < RPT; ++i) {
         const double xj = __shfl_sync(0xffffffffu, x[i], j);
         if (KEEP) xjs[i] = xj;
         double xi = x[i];
         if (i < DI) xi = (row_lo + i * WARPS + warp >= j) ? xi : 0.0;
-        if (i & 1) acc1 = fma(xj, xi, acc1); else acc0 = fma(xj, xi, acc0);
+        acc[i & 7] = fma(xj, xi, acc[i & 7]);
       }
-      red[par][warp][lane] = acc0 + acc1;
+      red[par][warp][lane] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
       if (c == 0 && warp == (j & (WARPS - 1))) {  // row j of the panel = slot i = j / WARPS of this warp
         double v = 0.0;
 #pragma unroll
@@ -111,18 +114,33 @@ __global__ void __launch_bounds__(WARPS * 32, 1) qr_panel_kernel(double* __restr
     __syncthreads();
     double gk = 0.0, gj = 0.0, rjk, alpha;
     if (C == 1) {
+      double pk[WARPS], pj[WARPS];
 #pragma unroll
       for (int w = 0; w < WARPS; ++w) {
-        gk += red[par][w][lane];
-        gj += red[par][w][j];
+        pk[w] = red[par][w][lane];
+        pj[w] = red[par][w][j];
       }
+#pragma unroll
+      for (int st = 1; st < WARPS; st *= 2)
+#pragma unroll
+        for (int w = 0; w + st < WARPS; w += 2 * st) {
+          pk[w] += pk[w + st];
+          pj[w] += pj[w + st];
+        }
+      gk = pk[0];
+      gj = pj[0];
       rjk = rowj[par][lane];
       alpha = rowj[par][j];
     } else {
       if (warp == 0) {
-        double g = 0.0;
+        double pk[WARPS];
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) g += red[par][w][lane];
+        for (int w = 0; w < WARPS; ++w) pk[w] = red[par][w][lane];
+#pragma unroll
+        for (int st = 1; st < WARPS; st *= 2)
+#pragma unroll
+          for (int w = 0; w + st < WARPS; w += 2 * st) pk[w] += pk[w + st];
+        const double g = pk[0];
         const double rj = (c == 0) ? rowj[par][lane] : 0.0;
         for (int dst = 0; dst < C; ++dst) {
           double* remote = cluster.map_shared_rank(&slots[0][0][0], dst);
@@ -147,13 +165,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) qr_panel_kernel(double* __restr
     } else {
       // beta = -sign(alpha) |x|, tau = (beta - alpha) / beta = 1 + |alpha| / |x|, scale = 1 / (alpha - beta): one rsqrt and one
       // reciprocal instead of a square root and two divisions on the critical path of the column
-      double rn = rsqrt(gj);
-      rn = rn * (1.5 - 0.5 * gj * rn * rn);   // one Newton step: full double precision whatever rsqrt's last bit does
+      const double rn = rsqrt(gj);            // 1 / |x|
       const double nrm = gj * rn;
       const double aabs = fabs(alpha);
       beta = alpha >= 0.0 ? -nrm : nrm;
-      tau = 1.0 + aabs * rn;
-      const double inv = 1.0 / (aabs + nrm);
+      tau = fma(aabs, rn, 1.0);
+      const double inv = __drcp_rn(aabs + nrm);
       scale = alpha >= 0.0 ? inv : -inv;
     }
     const double y = (gk - beta * rjk) * scale;  // k > j: v^T a_k;  k < j: V_k^T v_j
@@ -321,13 +338,11 @@ __global__ void __launch_bounds__(ATHREADS, 1) qr_apply_kernel(const double* __r
   __syncthreads();
   for (int e = tid; e < WSZ; e += ATHREADS) {
     const int i = e / QNC, cc = e % QNC;
-    double s = 0.0;
-    if (transT) {
-      for (int k = 0; k <= i; ++k) s += Tsm[k * QNB + i] * Wtot[k * QNC + cc];
-    } else {
-      for (int k = i; k < QNB; ++k) s += Tsm[i * QNB + k] * Wtot[k * QNC + cc];
-    }
-    W2[e] = -s;
+    // T is upper triangular and zero-padded: the full 32-term product with 4 independent accumulators (short FP64 chains)
+    double s4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < QNB; ++k) s4[k & 3] = fma(transT ? Tsm[k * QNB + i] : Tsm[i * QNB + k], Wtot[k * QNC + cc], s4[k & 3]);
+    W2[e] = -((s4[0] + s4[1]) + (s4[2] + s4[3]));
   }
   __syncthreads();
   // ---- phase 2: C += V W2 on this CTA's rows (M = rows, N = 32, K = 32; warps take groups of 8 rows) ----
