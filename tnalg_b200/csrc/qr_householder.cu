@@ -55,9 +55,19 @@ __device__ __forceinline__ double warp_sum_q(double v) {
 // column-j broadcast is a warp shuffle and the rank-1 update touches registers only; shared memory carries just the
 // cross-warp / cross-CTA partial sums (double-buffered by the parity of j: ONE CTA barrier -- plus one cluster barrier when
 // the panel spans several CTAs -- per column).
+#ifdef TN_QR_TIMING
+__device__ long long g_qr_clk[8];
+#define QR_CLK(slot) do { if (threadIdx.x == 0 && blockIdx.x == 0) { long long now_ = clock64(); g_qr_clk[slot] += now_ - tclk_; tclk_ = now_; } } while (0)
+#else
+#define QR_CLK(slot) do { } while (0)
+#endif
+
 template <int RPT, bool KEEP, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) qr_panel_kernel(double* __restrict__ W, int ld, int m, int j0, int nbp,
                                                                double* __restrict__ tau_out, double* __restrict__ T_out) {
+#ifdef TN_QR_TIMING
+  long long tclk_ = clock64();
+#endif
   cg::cluster_group cluster = cg::this_cluster();
   const int C = (int)cluster.num_blocks(), c = (int)cluster.block_rank();
   __shared__ double red[2][WARPS][QNB];        // per-warp partial Gram rows
@@ -84,7 +94,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) qr_panel_kernel(double* __restr
   if (tid < QNB) taus[tid] = 0.0;
   __syncthreads();
   if (C > 1) cluster.sync();  // every CTA of the cluster is resident before remote shared memory is written
+  QR_CLK(0);
 
+  double myscale = 0.0;  // 1 / (alpha - beta) of column `lane`: the reflector tails stay unscaled in the registers until the write-back
   for (int j = 0; j < nbp; ++j) {
     const int par = j & 1;
     // ---- row j of the panel Gram matrix, g_k = sum_{rows >= j} P[r,j] P[r,k], over this thread's rows ----
@@ -111,7 +123,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) qr_panel_kernel(double* __restr
         rowj[par][lane] = v;
       }
     }
+    QR_CLK(1);
     __syncthreads();
+    QR_CLK(2);
     double gk = 0.0, gj = 0.0, rjk, alpha;
     if (C == 1) {
       double pk[WARPS], pj[WARPS];
@@ -156,6 +170,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) qr_panel_kernel(double* __restr
       rjk = slots[par][0][QNB + lane];
       alpha = slots[par][0][QNB + j];
     }
+    QR_CLK(3);
     double tau, beta, scale;
     // nothing below the diagonal, or a column that is zero to the underflow threshold (its sum of squares would be formed from
     // denormal products: exactly dependent columns shrink by 1e-16 per reflector under FMA and get there): H = 1, as dlarfg
@@ -173,12 +188,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) qr_panel_kernel(double* __restr
       const double inv = __drcp_rn(aabs + nrm);
       scale = alpha >= 0.0 ? inv : -inv;
     }
-    const double y = (gk - beta * rjk) * scale;  // k > j: v^T a_k;  k < j: V_k^T v_j
+    // k > j: v^T a_k;  k < j: V_k^T v_j (column k holds the unscaled tail u_k = v_k / myscale_k)
+    const double y = (gk - beta * rjk) * scale * (lane < j ? myscale : 1.0);
     const double ty = tau * y;
+    if (lane == j) myscale = scale;
     // ---- apply H_j to the columns k > j (registers only), store v below the diagonal and beta on it ----
-    // x[r,k] -= (tau y_k scale) x[r,j] for k > j: the coefficient is zero in the lanes k <= j, so rows below the diagonal block
-    // need one FMA and one predicated multiply (lane j: v_r = x[r,j] scale) with no branch
+    // x[r,k] -= (tau y_k scale) x[r,j] for k > j: the coefficient is zero in the lanes k <= j (column j keeps its unscaled tail), so
+    // rows below the diagonal block need exactly one FMA and no branch
     const double coef = lane > j ? ty * scale : 0.0;
+    QR_CLK(4);
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
       const double xj = KEEP ? xjs[i] : __shfl_sync(0xffffffffu, x[i], j);
@@ -186,45 +204,93 @@ __global__ void __launch_bounds__(WARPS * 32, 1) qr_panel_kernel(double* __restr
         const int pr = row_lo + i * WARPS + warp;
         if (pr > j) {
           x[i] = fma(-coef, xj, x[i]);
-          if (lane == j) x[i] = xj * scale;
         } else if (pr == j) {
           if (lane > j) x[i] -= ty;
           else if (lane == j) x[i] = beta;
         }
       } else {
         x[i] = fma(-coef, xj, x[i]);
-        if (lane == j) x[i] = xj * scale;
       }
     }
     if (c == 0 && warp == (j & (WARPS - 1))) {  // the warp that owns row j records the T-factor inputs
       if (lane < j) Z[lane * QNB + j] = y;
       if (lane == j) taus[j] = tau;
     }
+    QR_CLK(5);
   }
   __syncthreads();
 
-  // ---- compact-WY factor: T[j,j] = tau_j, T[0:j, j] = -tau_j T[0:j,0:j] Z[0:j, j]  (dlarft, forward columnwise) ----
+  // ---- compact-WY factor.  T^-1 = S with S_jj = 1 / tau_j and S_ij = V_i^T V_j = Z[i][j] for i < j (from T^-1 + T^-T = V^T V),
+  // so T is the inverse of a 32 x 32 upper-triangular matrix: recursive doubling over diagonal blocks of size 1, 2, 4, 8, 16,
+  //   [[A, B], [0, D]]^-1 = [[A^-1, -A^-1 B D^-1], [0, D^-1]],
+  // every level a batch of tiny products done by the whole CTA (the column-by-column dlarft recurrence is a chain of 32
+  // dependent steps, 16 us at FP64 latencies).  A reflector with tau = 0 (H = 1) decouples: S_jj = 1, row / column j of Z zero,
+  // T_jj = 0 afterwards.
   if (c == 0) {
-    for (int j = 0; j < nbp; ++j) {
-      const double tj = taus[j];
-      for (int i = warp; i < j; i += WARPS) {
-        double s = (lane >= i && lane < j) ? Ts[i * QNB + lane] * Z[lane * QNB + j] : 0.0;
-        s = warp_sum_q(s);
-        if (lane == 0) Ts[i * QNB + j] = -tj * s;
+    const int nt = WARPS * 32;
+    for (int idx = tid; idx < QNB * QNB; idx += nt) {
+      const int i = idx >> 5, j = idx & 31;
+      const bool off = i < nbp && j < nbp && taus[i] != 0.0 && taus[j] != 0.0;
+      Ts[idx] = (i == j) ? ((i < nbp && taus[i] != 0.0) ? taus[i] : 1.0) : ((i < j && off) ? Z[idx] : 0.0);  // diag: A^-1 of the 1x1 blocks
+    }
+    __syncthreads();
+    for (int sz = 1; sz < QNB; sz *= 2) {
+      // block pair p: A = rows/cols [2p*sz, 2p*sz+sz), D = [2p*sz+sz, 2p*sz+2sz), B = A-rows x D-cols (still holds S)
+      // step 1: Y = B D^-1 (kept in Z as scratch);  step 2: X = -A^-1 Y, written over B
+      for (int e = tid; e < (QNB / (2 * sz)) * sz * sz; e += nt) {
+        const int p = e / (sz * sz), r = (e / sz) % sz, q = e % sz;
+        const int a0 = 2 * p * sz, d0 = a0 + sz;
+        double acc0 = 0.0, acc1 = 0.0;
+        for (int l = 0; l <= q; ++l) {  // D^-1 is upper triangular
+          const double pr = Ts[(a0 + r) * QNB + d0 + l] * Ts[(d0 + l) * QNB + d0 + q];
+          if (l & 1) acc1 += pr; else acc0 += pr;
+        }
+        Z[(a0 + r) * QNB + d0 + q] = acc0 + acc1;
       }
-      if (tid == 0) Ts[j * QNB + j] = tj;
+      __syncthreads();
+      for (int e = tid; e < (QNB / (2 * sz)) * sz * sz; e += nt) {
+        const int p = e / (sz * sz), r = (e / sz) % sz, q = e % sz;
+        const int a0 = 2 * p * sz, d0 = a0 + sz;
+        double acc0 = 0.0, acc1 = 0.0;
+        for (int l = r; l < sz; ++l) {  // A^-1 is upper triangular
+          const double pr = Ts[(a0 + r) * QNB + a0 + l] * Z[(a0 + l) * QNB + d0 + q];
+          if (l & 1) acc1 += pr; else acc0 += pr;
+        }
+        Ts[(a0 + r) * QNB + d0 + q] = -(acc0 + acc1);
+      }
       __syncthreads();
     }
-    for (int idx = tid; idx < QNB * QNB; idx += (WARPS * 32)) T_out[idx] = Ts[idx];
+    for (int idx = tid; idx < QNB * QNB; idx += nt) {
+      const int i = idx >> 5, j = idx & 31;
+      const bool dead = (i == j) && !(i < nbp && taus[i] != 0.0);
+      T_out[idx] = dead ? 0.0 : Ts[idx];
+    }
     if (tid < nbp) tau_out[j0 + tid] = taus[tid];
   }
+  QR_CLK(6);
 #pragma unroll
   for (int i = 0; i < RPT; ++i) {
     const int pr = row_lo + i * WARPS + warp;
-    if (pr < rows_total && lane < nbp) W[(size_t)(j0 + pr) * ld + j0 + lane] = x[i];
+    if (pr < rows_total && lane < nbp) W[(size_t)(j0 + pr) * ld + j0 + lane] = pr > lane ? x[i] * myscale : x[i];  // v below the diagonal
   }
   if (C > 1) cluster.sync();  // no CTA exits while a peer may still address its shared memory
+  QR_CLK(7);
 }
+
+#ifdef TN_QR_TIMING
+extern "C" int tn_qr_debug_clocks(long long* out8, int reset) {
+  long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (out8) {
+    if (cudaMemcpyFromSymbol(h, g_qr_clk, sizeof(h)) != cudaSuccess) return -2;
+    for (int i = 0; i < 8; ++i) out8[i] = h[i];
+  }
+  if (reset) {
+    long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyToSymbol(g_qr_clk, z, sizeof(z)) != cudaSuccess) return -2;
+  }
+  return 0;
+}
+#endif
 
 // Cm[j0:m, c_begin:c_end] <- (1 - V op(T) V^T) Cm[j0:m, c_begin:c_end];  transT != 0: op(T) = T^T.
 // One cluster per strip of QNC = 32 columns; the CTAs of the cluster split the rows (RB each).  The kernel is a chain of
