@@ -43,6 +43,12 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
+// cluster-wide barrier with release / acquire ordering at CLUSTER scope.  cooperative_groups' cluster_barrier() emits a GPU-scope
+// fence (MEMBAR.ALL.GPU) in front of the hardware barrier, which dominated the per-column exchange of the panel kernel.
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
 __device__ __forceinline__ double warp_sum_q(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -93,7 +99,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) qr_panel_kernel(double* __restr
   }
   if (tid < QNB) taus[tid] = 0.0;
   __syncthreads();
-  if (C > 1) cluster.sync();  // every CTA of the cluster is resident before remote shared memory is written
+  if (C > 1) cluster_barrier();  // every CTA of the cluster is resident before remote shared memory is written
   QR_CLK(0);
 
   double myscale = 0.0;  // 1 / (alpha - beta) of column `lane`: the reflector tails stay unscaled in the registers until the write-back
@@ -162,7 +168,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) qr_panel_kernel(double* __restr
           remote[(par * QMAXC + c) * QSLOT + QNB + lane] = rj;
         }
       }
-      cluster.sync();
+      cluster_barrier();
       for (int s = 0; s < C; ++s) {
         gk += slots[par][s][lane];
         gj += slots[par][s][j];
@@ -273,7 +279,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) qr_panel_kernel(double* __restr
     const int pr = row_lo + i * WARPS + warp;
     if (pr < rows_total && lane < nbp) W[(size_t)(j0 + pr) * ld + j0 + lane] = pr > lane ? x[i] * myscale : x[i];  // v below the diagonal
   }
-  if (C > 1) cluster.sync();  // no CTA exits while a peer may still address its shared memory
+  if (C > 1) cluster_barrier();  // no CTA exits while a peer may still address its shared memory
   QR_CLK(7);
 }
 
@@ -349,7 +355,7 @@ __global__ void __launch_bounds__(ATHREADS, 1) qr_apply_kernel(const double* __r
       }
     }
   }
-  if (CR > 1) cluster.sync();  // peers are resident (remote writes below); doubles as the CTA barrier
+  if (CR > 1) cluster_barrier();  // peers are resident (remote writes below); doubles as the CTA barrier
   else __syncthreads();
 
   // ---- phase 1: tile (mt, 2 n-tiles) of W = V^T C over all rows of this CTA; 4 interleaved accumulators per tile ----
@@ -395,7 +401,7 @@ __global__ void __launch_bounds__(ATHREADS, 1) qr_apply_kernel(const double* __r
       }
     }
   }
-  if (CR > 1) cluster.sync(); else __syncthreads();
+  if (CR > 1) cluster_barrier(); else __syncthreads();
   for (int e = tid; e < WSZ; e += ATHREADS) {  // total over the CTAs in rank order
     double s = 0.0;
     for (int src = 0; src < CR; ++src) s += Wex[src * WSZ + e];
@@ -455,7 +461,7 @@ __global__ void __launch_bounds__(ATHREADS, 1) qr_apply_kernel(const double* __r
       }
     }
   }
-  if (CR > 1) cluster.sync();  // no CTA exits while a peer may still write its exchange slots
+  if (CR > 1) cluster_barrier();  // no CTA exits while a peer may still write its exchange slots
 }
 
 // out (rows x cols, ld ldo) = in^T or in;  tiled through shared memory
