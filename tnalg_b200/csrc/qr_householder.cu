@@ -20,6 +20,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdint>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -47,6 +48,35 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 // fence (MEMBAR.ALL.GPU) in front of the hardware barrier, which dominated the per-column exchange of the panel kernel.
 __device__ __forceinline__ void cluster_barrier() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+// ---- asynchronous cluster exchange: remote shared-memory stores that signal an mbarrier of the destination CTA (STAS) ----
+__device__ __forceinline__ unsigned smem_u32q(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init_q(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32q(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx_q(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32q(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_q(uint64_t* bar, unsigned parity) {
+  unsigned done = 0, spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(smem_u32q(bar)), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1u << 26)) __trap();  // a lost signal must abort the kernel, not hang the GPU
+  }
+}
+// 8-byte store into the shared memory of CTA `dst` of the cluster; completes 8 bytes on that CTA's mbarrier `bar`
+__device__ __forceinline__ void st_async_q(double* local_addr, double v, uint64_t* bar, unsigned dst) {
+  unsigned ra, rb;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32q(local_addr)), "r"(dst));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(smem_u32q(bar)), "r"(dst));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(ra), "d"(v), "r"(rb) : "memory");
 }
 
 __device__ __forceinline__ double warp_sum_q(double v) {
@@ -82,6 +112,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) qr_panel_kernel(double* __restr
   __shared__ double Z[QNB * QNB];               // Z[k*32 + j] = V_k^T v_j (k < j)
   __shared__ double Ts[QNB * QNB];              // compact-WY factor
   __shared__ double taus[QNB];
+  __shared__ uint64_t xbar[2];                  // arrival of the C contributions of a column (double-buffered like the slots)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int DI = (QNB / WARPS) < RPT ? (QNB / WARPS) : RPT;  // slots that may hold rows of the diagonal block (panel rows < 32)
   const int rows_total = m - j0;
@@ -98,8 +129,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) qr_panel_kernel(double* __restr
     Ts[idx] = 0.0;
   }
   if (tid < QNB) taus[tid] = 0.0;
+  if (tid == 0) {
+    mbar_init_q(&xbar[0], 1);
+    mbar_init_q(&xbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
-  if (C > 1) cluster_barrier();  // every CTA of the cluster is resident before remote shared memory is written
+  if (C > 1) cluster_barrier();  // every CTA of the cluster is resident (and its mbarriers live) before remote stores start
   QR_CLK(0);
 
   double myscale = 0.0;  // 1 / (alpha - beta) of column `lane`: the reflector tails stay unscaled in the registers until the write-back
@@ -162,13 +198,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) qr_panel_kernel(double* __restr
           for (int w = 0; w + st < WARPS; w += 2 * st) pk[w] += pk[w + st];
         const double g = pk[0];
         const double rj = (c == 0) ? rowj[par][lane] : 0.0;
+        // this CTA's partial row goes to slot c of every CTA (itself included) with asynchronous remote stores that count on
+        // the destination's mbarrier: no cluster-wide barrier and no fence on the per-column path (barrier.cluster with release
+        // semantics costs a GPU-scope MEMBAR plus an L1 invalidate, ~1600 cycles per column)
+        if (lane == 0) mbar_expect_tx_q(&xbar[par], (unsigned)(C * QSLOT * sizeof(double)));
         for (int dst = 0; dst < C; ++dst) {
-          double* remote = cluster.map_shared_rank(&slots[0][0][0], dst);
-          remote[(par * QMAXC + c) * QSLOT + lane] = g;
-          remote[(par * QMAXC + c) * QSLOT + QNB + lane] = rj;
+          st_async_q(&slots[par][c][lane], g, &xbar[par], (unsigned)dst);
+          st_async_q(&slots[par][c][QNB + lane], rj, &xbar[par], (unsigned)dst);
         }
       }
-      cluster_barrier();
+      mbar_wait_q(&xbar[par], (unsigned)((j >> 1) & 1));
       for (int s = 0; s < C; ++s) {
         gk += slots[par][s][lane];
         gj += slots[par][s][j];
