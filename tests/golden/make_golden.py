@@ -21,6 +21,8 @@ Cases
   pr_fixtures      numbers extracted from the reference's own data_dmrg/*.pr result pickles
   docstring_kats   integer known-answer vectors printed in TensorBasicModule.py docstrings
   truncation_lib   library/ generation: truncate_virtual_bonds(chi=5) of a random chi=12 MPS (kept spectrum, tensors)
+  idmrg_white_xxz  library/ generation: White-style two-site iDMRG (energy per sweep, Schmidt values, two-site handle per call)
+  tebd_chain6      library/ generation: tebd_standard on an XXZ chain in a field, L=6 chi=8 (final MPS, energies, magnetisation)
 """
 import os
 import pickle
@@ -275,6 +277,78 @@ def tensor_kats():
     return out
 
 
+def _library_modules():
+    """the package-style generation (library/, algorithms/) under the same shim"""
+    import importlib
+    import types
+    if 'matplotlib.cm' not in sys.modules:
+        sys.modules['matplotlib.cm'] = types.ModuleType('matplotlib.cm')
+        sys.modules['matplotlib'].cm = sys.modules['matplotlib.cm']
+    return (importlib.import_module('library.MPSClass'), importlib.import_module('library.Parameters'),
+            importlib.import_module('algorithms.DMRG_anyH'), importlib.import_module('algorithms.TEBDalgo'))
+
+
+def idmrg_white_case():
+    """f1 + f3: the reference's White-style TWO-SITE iDMRG (algorithms/DMRG_anyH.py:106-176 driving library/MPSClass.py
+    MpsInfinite: term-summed two-site matvec :1688-1707, SVD truncation :1676-1686) on an XXZ chain in a tilted field (no
+    symmetry multiplets, so the truncation is unambiguous): the bond energy after every sweep for 40 sweeps from seed 0, the
+    final Schmidt values, and per-call vectors of the two-site handle and of the dense effective Hamiltonian on the final blocks."""
+    import contextlib
+    import io
+    import re
+    lib, pml, alg, _ = _library_modules()
+    para = pml.generate_parameters_infinite_dmrg()
+    para.update(dmrg_type=sys.intern('white'), jxy=1, jz=0.5, hx=0.3, hz=0.1, chi=10, n_site=2, sweep_time=40, dt_ob=1,
+                break_tol=1e-14, form=sys.intern('center_ort'))
+    with contextlib.redirect_stdout(io.StringIO()):
+        para = pml.make_para_consistent_idmrg(para)
+    np.random.seed(0)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        A, ob, info = alg.dmrg_infinite_size(para)
+    eb = np.array([float(x) for x in re.findall(r'Eb = (-?[0-9.e+-]+)', buf.getvalue())])
+    assert eb.size == 40
+    out = {'seed': 0, 'chi': 10, 'd': 2, 'tau': para['tau'], 'jxy': 1.0, 'jz': 0.5, 'hx': 0.3, 'hz': 0.1, 'sweep_time': 40,
+           'hamilt_index': np.asarray(para['hamilt_index'], dtype=float), 'eb_history': eb, 'eb': ob['eb'], 'lm': np.asarray(A.lm[0]),
+           'bath': np.real(A.bath_op_onsite), 'eff_ops': np.stack([np.real(np.asarray(o)) for o in A.effective_ops]),
+           'op': np.stack([np.asarray(o, dtype=complex) for o in A.operators])}
+    psi = np.random.RandomState(7).randn(10, 2, 2, 10)
+    out['psi'] = psi
+    out['handle_out'] = np.real(A.update_central_tensor_effective_ops_fh(psi.reshape(-1), para['tau'])).reshape(-1)
+    out['heff_dense'] = np.real(A.effective_hamilt_from_op())
+    return out
+
+
+def tebd_case():
+    """f3: the reference's tebd_standard (algorithms/TEBDalgo.py:11-90; gates :38-46, MpsStandardTEBD library/MPSClass.py:1408-1447)
+    on an XXZ chain in a field, L = 6, chi = 8 (exact), two time steps of 60 iterations from seed 2: final energies, magnetisation,
+    Schmidt spectrum."""
+    import contextlib
+    import io
+    lib, pml, _, tebd = _library_modules()
+    para = pml.generate_parameters_standard_tebd()
+    para.update(l=6, chi=8, jxy=1, jz=0.6, hx=0.25, hz=0.1, tau0=0.1, dtau=0.5, taut=2, dt_ob=10, iterate_time=60, if_break=True,
+                break_tol=1e-30, save_mode=sys.intern('final'))
+    para = pml.make_para_consistent_tebd(para)
+    np.random.seed(2)
+    with contextlib.redirect_stdout(io.StringIO()):
+        mps = lib.MpsStandardTEBD(para['l'], para['d'], para['chi'], para['spin'], evolve_way='gates')
+        ini = [t.copy() for t in mps.mps]
+    np.random.seed(2)
+    with contextlib.redirect_stdout(io.StringIO()):
+        mps, ob, para = tebd.tebd_standard(para)
+    out = {'seed': 2, 'l': 6, 'chi': 8, 'd': 2, 'jxy': 1.0, 'jz': 0.6, 'hx': 0.25, 'hz': 0.1, 'tau0': 0.1, 'dtau': 0.5, 'taut': 2,
+           'iterate_time': 60, 'n_obs': len(ob['e_site'])}
+    for n, t in enumerate(ini):
+        out['ini_%d' % n] = t
+    for n, t in enumerate(mps.mps):
+        out['mps_%d' % n] = np.real(t)
+    out['center'] = mps.center
+    for k in ('e_site', 'mx', 'mz', 'eb'):
+        out[k] = np.real(np.asarray(ob[k][-1], dtype=complex)).astype(float) if len(ob[k]) else np.zeros(0)
+    return out
+
+
 def lattice_para(lattice, **kw):
     para = Pm.generate_parameters_dmrg(lattice)
     para.update(kw)
@@ -300,6 +374,8 @@ def main():
         'truncation_lib': truncation_case,
         'rdm_xxz8': rdm_case,
         'tensor_kats': tensor_kats,
+        'idmrg_white_xxz': idmrg_white_case,
+        'tebd_chain6': tebd_case,
     }
     only = sys.argv[1:]
     for name, fn in cases.items():

@@ -417,3 +417,16 @@ def test_huge_norms_do_not_overflow(be):
     A.mps[2] = A.mps[2] * 1e299
     A.update_tensor_eigs(2, para['index1'], para['index2'], para['coeff1'], para['coeff2'], para['tau'], True, tol=1e-10)
     assert A.last_eig['converged'] and abs(A.norm_mps() - 1) < 1e-12
+
+
+def test_idmrg_white_two_site_vs_reference_gpu(be, golden):
+    """f1 + f3 on the CUDA path: the reference's two-site handle / dense two-site H_eff per call, and the White-style iDMRG
+    trajectory (tests/test_idmrg_tebd_cpu.py::check_idmrg, goldens from the unmodified reference)"""
+    from tests.test_idmrg_tebd_cpu import check_idmrg
+    check_idmrg(golden, be)
+
+
+def test_tebd_standard_vs_reference_gpu(be, golden):
+    """f3 on the CUDA path: tebd_standard against the reference's evolved state and observables"""
+    from tests.test_idmrg_tebd_cpu import check_tebd
+    check_tebd(golden, be)

@@ -126,6 +126,48 @@ def dmrg_finite_size_two_site(para=None, chi_init=None, quiet=True):
     return ob, A, info, para
 
 
+def dmrg_infinite_size(para=None, A=None, hamilt=None, quiet=True):
+    """White-style two-site iDMRG on the CUDA kernels: the driver of algorithms/DMRG_anyH.py:106-176 for dmrg_type='white',
+    n_site=2 (the MPO form is not provided).  Returns (A, ob, info) like the reference; ob['eb'] is the energy of the central
+    bond at the last observation, ob['eb_history'] every observed value."""
+    from .HamiltonianModule import hamiltonian_heisenberg_library
+    from .MPSClass import MpsInfinite
+    t_start = time.time()
+    if para is None:
+        para = pm.generate_parameters_infinite_dmrg()
+        para.update(dmrg_type='white')
+        para = pm.make_para_consistent_idmrg(para)
+    say = (lambda *a: None) if quiet else print
+    if hamilt is None:
+        hamilt = hamiltonian_heisenberg_library(para['spin'], para['jxy'], para['jxy'], para['jz'], para['hx'] / 2, para['hz'] / 2)
+    if A is None:
+        A = MpsInfinite(para['form'], para['d'], para['chi'], para['d'] ** para['n_site'], n_site=para['n_site'],
+                        is_symme_env=para['is_symme_env'], dmrg_type=para['dmrg_type'], hamilt_index=para['hamilt_index'])
+    e0, e1, de, history = 0.0, 1.0, 1.0, []
+    A.update_ort_tensor_mps('left')
+    A.update_bath_onsite()
+    A.update_effective_ops()
+    for t in range(0, para['sweep_time']):
+        A.update_central_tensor((para['tau'], 'full'))
+        if t % para['dt_ob'] == 0:
+            A.rho_from_central_tensor()
+            e1 = A.observe_energy(hamilt)
+            history.append(e1)
+            say('At the %g-th sweep: Eb = %s' % (t, e1))
+            de = abs(e0 - e1) / A.n_site
+            if de > para['break_tol']:
+                e0 = e1
+            else:
+                say('Converged with de = %g' % de)
+                break
+        A.update_ort_tensor_mps('left')
+        A.update_bath_onsite()
+        A.update_effective_ops()
+    ob = {'eb': e1, 'eb_history': np.array(history)}
+    info = {'t_cost': time.time() - t_start, 'n_matvec': A.stats['n_matvec'], 'n_solves': A.stats['n_solves']}
+    return A, ob, info
+
+
 def run_parameter_scan(paras, save=True, seed=None, two_site=False):
     """Independent DMRG runs over a list of para dicts, distributed over the ranks of torch.distributed (run n goes to rank
     n mod world; no collective on the data path -- the pattern of the reference's ScriptRun/DMRG/runDMRGfull.py:27-39, 110

@@ -103,3 +103,21 @@ def interactions_full_connection_two_body(l):
     """([first_site, second_site] for every pair n1 < n2, number of pairs) (HamiltonianModule.py:137-148)"""
     pairs = np.array([[n1, n2] for n1 in range(l) for n2 in range(n1 + 1, l)], dtype=float).reshape(-1, 2)
     return pairs, float(pairs.shape[0])
+
+
+def hamiltonian_heisenberg_library(spin, jx, jy, jz, hx, hz):
+    """the library generation's two-site Hamiltonian (library/HamiltonianModule.py:141-147): the fields enter with a MINUS sign,
+    jx SxSx + jy SySy + jz SzSz - hx (Sx1 + Sx2) - hz (Sz1 + Sz2).  Used by the iDMRG / TEBD drivers of that generation."""
+    return hamiltonian_heisenberg(spin, jx, jy, jz, -hx, -hz)
+
+
+def hamiltonian_indexes(model, parameters):
+    """rows [op1, op2, coupling] of a two-site Hamiltonian in the operator order I, sx, sy, sz, su, sd
+    (library/HamiltonianModule.py:97-135).  'heisenberg': parameters = (j_ud, j_zz, h_x, h_z); 'q-ising': (j_zz, h_x)."""
+    if model == 'heisenberg':
+        j, jz, hx, hz = parameters
+        return np.array([[4, 5, j], [5, 4, j], [3, 3, jz], [0, 1, hx], [1, 0, hx], [0, 3, hz], [3, 0, hz]], dtype=float)
+    if model == 'q-ising':
+        jz, hx = parameters
+        return np.array([[3, 3, jz], [0, 1, hx], [1, 0, hx]], dtype=float)
+    raise ValueError('hamiltonian_indexes: unknown model %r' % (model,))

@@ -680,3 +680,257 @@ class MpsOpenBoundaryClass(MpsBasic):
         self.pool = None
         self._env = None
         self._env_key = None
+
+
+class MpsInfinite(MpsBasic):
+    """White-style two-site iDMRG state on the CUDA kernels: the part of the reference's MpsInfinite
+    (library/MPSClass.py:1560-1870) with dmrg_type='white', n_site=2, form='center_ort', symmetric environments.
+
+    Same constructor signature and method names.  mps[1] is the central two-site tensor (chi, d, d, chi); mps[0] / mps[2] the
+    left-orthonormal tensors of the last split; bath_op_onsite and effective_ops[n] the block Hamiltonian and the block
+    operators of the growing half-chain.  update_central_tensor solves the two-site effective Hamiltonian
+    (update_central_tensor_effective_ops_fh, :1688-1707 -- a term-summed two-site matvec, here one tn_effh_plan with the combined
+    physical index d*d) with the device-resident Lanczos; update_ort_tensor_mps is the SVD truncation (:1676-1686) on the
+    Jacobi kernel.  The MPO-form iDMRG (dmrg_type='mpo') is not provided (out of scope)."""
+
+    def __init__(self, form, d, chi, D, n_tensor=3, n_site=1, spin='half', dmrg_type='mpo', way='qr', operators=None,
+                 hamilt_index=None, is_symme_env=True, is_real=True, debug=False):
+        MpsBasic.__init__(self)
+        if dmrg_type != 'white' or n_site != 2 or form != 'center_ort':
+            raise NotImplementedError("MpsInfinite: only dmrg_type='white', n_site=2, form='center_ort' run on the CUDA path")
+        if hamilt_index is None:
+            raise ValueError('MpsInfinite: hamilt_index (rows [op1, op2, coupling]) is required')
+        self._be = _ops.backend()
+        self.spin, self.n_tensor, self.n_site = spin, 3, n_site
+        self.d, self.chi, self.D, self.form = d, chi, D, form
+        self.decomp_way, self.is_symme_env, self.is_real, self._debug, self.dmrg_type = way, True, is_real, debug, dmrg_type
+        self.orthogonality = np.array([-1, 0, 1])
+        self.is_center_ort, self.is_canonical = True, False
+        if operators is None:
+            op_half = spin_operators(spin)
+            self.operators = [op_half['id'], op_half['sx'], op_half['sy'], op_half['sz'], op_half['su'], op_half['sd']]
+        else:
+            self.operators = operators
+        self.hamilt_index = np.asarray(hamilt_index, dtype=float).reshape(-1, 3)
+        self.op_index = set()
+        self.simplified_op_index()
+        be = self._be
+        # randomly initialised central tensor, same draw as initialize_imps (:1618-1624)
+        psi = np.random.randn(chi, d, d, chi)
+        psi /= np.linalg.norm(psi.reshape(-1))
+        self.mps = [None, be.from_numpy(psi.reshape(chi, d * d, chi)), None]
+        self.lm = [np.zeros(0)] * 3
+        self.rho = None
+        self.update_ort_tensor_mps('both')
+        self.bath_op_onsite = be.from_numpy(np.eye(chi))
+        self.effective_ops = [be.from_numpy(np.eye(chi)) for _ in range(len(self.operators))]
+        self.stats = {'n_solves': 0, 'n_matvec': 0}
+        self.lanczos_ncv, self.lanczos_max_restarts = 20, 2000
+
+    def _real_op(self, n):
+        o = np.asarray(self.operators[int(n)])
+        if np.abs(np.imag(o)).max() != 0:
+            raise ValueError('operator %d is complex; the real path supports real site operators only' % int(n))
+        return np.real(o).astype(float)
+
+    def simplified_op_index(self):
+        """the operators whose block versions are needed (:1643-1649)"""
+        self.op_index = {1, 3}
+        for n in range(self.hamilt_index.shape[0]):
+            self.op_index.add(int(self.hamilt_index[n, 0]))
+            self.op_index.add(int(self.hamilt_index[n, 1]))
+
+    def update_ort_tensor_mps(self, which='both', dc=None):
+        """split the central tensor: theta (chi*d, d*chi) = U S Vh truncated to dc (:1676-1686);
+        mps[0] = U (chi, d, dc), mps[2][b, s, k] = Vh[k, (s, b)]"""
+        be = self._be
+        chi, d = self.mps[1].shape[0], self.d
+        b = self.mps[1].shape[2]
+        dc = min(self.chi, chi * d) if dc is None else min(dc, chi * d)
+        U, S, Vt = be.svd(self.mps[1].reshape(chi * d, d * b), k_keep=dc)
+        self.mps[0] = U.contiguous().reshape(chi, d, dc)
+        self.mps[2] = Vt.reshape(dc, d, b).permute(2, 1, 0).contiguous()
+        self.lm[0] = be.to_numpy(S)
+
+    def update_effective_ops(self, which='op_index'):
+        """effective_ops[n] = block operator n grown by one site (:1762-1779), all of them in one batched tn_env_update"""
+        idx = sorted(self.op_index) if which == 'op_index' else ([which] if isinstance(which, int) else list(which))
+        idx = [n for n in idx if np.abs(np.imag(np.asarray(self.operators[n]))).max() == 0]
+        outs = self._be.env_update(0, self.mps[0], [[(None, self._real_op(n))] for n in idx])
+        for n, mat in zip(idx, outs):
+            self.effective_ops[n] = mat
+
+    def update_bath_onsite(self):
+        """block Hamiltonian of the half-chain grown by one site (:1781-1790): one output with 1 + #terms links"""
+        links = [(self.bath_op_onsite, None)]
+        for n in range(self.hamilt_index.shape[0]):
+            i1, i2, j = int(self.hamilt_index[n, 0]), int(self.hamilt_index[n, 1]), float(self.hamilt_index[n, 2])
+            if j != 0.0:
+                links.append((self.effective_ops[i1], j * self._real_op(i2)))
+        op = self._be.env_update(0, self.mps[0], [links])[0]
+        self.bath_op_onsite = (op + op.t()) / 2
+
+    def effective_plan(self):
+        """tn_effh_plan of the two-site effective Hamiltonian (update_central_tensor_effective_ops_fh, :1688-1707):
+        bath (x) 1 + 1 (x) bath + sum_n j_n op1 (x) op2 on the pair + sum_n j_n [block(op1) (x) op2 (x) 1 + 1 (x) op2 (x) block(op1)]"""
+        be, d, chi = self._be, self.d, self.mps[1].shape[0]
+        eye = np.eye(d)
+        M = np.zeros((d * d, d * d))
+        ls, rs = {}, {}
+        for n in range(self.hamilt_index.shape[0]):
+            i1, i2, j = int(self.hamilt_index[n, 0]), int(self.hamilt_index[n, 1]), float(self.hamilt_index[n, 2])
+            if j == 0.0:
+                continue
+            M += j * np.kron(self._real_op(i1), self._real_op(i2))
+            ls.setdefault(i2, []).append((j, i1))
+            rs.setdefault(i2, []).append((j, i1))
+        LS, ls_ops, RS, rs_ops = [], [], [], []
+        for i2, pairs in sorted(ls.items()):
+            mat = be.lincomb([self.effective_ops[i1] for _, i1 in pairs], [c for c, _ in pairs])
+            LS.append(mat)
+            ls_ops.append(np.kron(self._real_op(i2), eye))
+            RS.append(mat)
+            rs_ops.append(np.kron(eye, self._real_op(i2)))
+        return be.effh_plan((chi, d * d, self.mps[1].shape[2]), self.bath_op_onsite, self.bath_op_onsite, M, LS, ls_ops, RS, rs_ops)
+
+    def update_central_tensor_effective_ops_fh(self, psi, tau):
+        """psi -> psi - tau * H_eff psi on a (chi, d, d, chi) tensor given as numpy or device tensor (:1688-1707)"""
+        be = self._be
+        dev = hasattr(psi, 'data_ptr')
+        x = psi if dev else be.from_numpy(np.real(np.asarray(psi)))
+        plan = self.effective_plan()
+        y = plan.matvec(x.reshape(plan.shape), 1.0, -float(tau)).clone()
+        plan.destroy()
+        return y if dev else be.to_numpy(y).reshape(np.asarray(psi).shape)
+
+    def effective_hamilt_from_op(self):
+        """dense two-site effective Hamiltonian (:1709-1729), through the plan (small chi only)"""
+        be = self._be
+        plan = self.effective_plan()
+        n = int(np.prod(plan.shape))
+        if n > 4096:
+            plan.destroy()
+            raise ValueError('effective_hamilt_from_op: dimension %d too large for a dense matrix' % n)
+        h = np.zeros((n, n))
+        for j in range(n):
+            e = np.zeros(n)
+            e[j] = 1.0
+            h[:, j] = be.to_numpy(plan.matvec(be.from_numpy(e.reshape(plan.shape)), 0.0, 1.0)).reshape(-1)
+        plan.destroy()
+        return h
+
+    def update_central_tensor(self, inputs):
+        """dominant eigenvector of 1 - tau * H_eff as the new central tensor (:1840-1850); inputs = (tau, way) -- both ways
+        use the operator (plan) form here, the dense 'full' matrix of the reference is the same operator"""
+        tau = inputs[0] if isinstance(inputs, (tuple, list)) else float(inputs)
+        plan = self.effective_plan()
+        # The previous central tensor has a definite mirror parity; when the ground state of the grown block sits in the other
+        # sector it is EXACTLY orthogonal to it and no Krylov method started from it can reach it (the reference's ARPACK call
+        # gets there through round-off).  A 1e-6 admixture of a fixed pseudo-random vector keeps every sector in the Krylov space.
+        v0 = self.mps[1].reshape(-1)
+        noise = np.random.RandomState(1000 + self.stats['n_solves']).randn(v0.numel())
+        v0 = v0 + self._be.from_numpy(noise * (1e-6 / np.sqrt(noise.size)))
+        lam, vec, n_mv, resid, ok = self._be.lanczos(plan, tau, v0, 1e-14, ncv=self.lanczos_ncv,
+                                                     max_restarts=self.lanczos_max_restarts)
+        plan.destroy()
+        self.stats['n_solves'] += 1
+        self.stats['n_matvec'] += n_mv
+        self.mps[1] = vec.reshape(self.mps[1].shape)
+
+    def rho_from_central_tensor(self):
+        """two-site reduced density matrix of the central pair (:1852-1868), (d*d, d*d) on the host"""
+        t = self._be.to_numpy(self.mps[1])          # (chi, d*d, chi)
+        self.rho = np.einsum('asb,atb->st', t, t)
+        return self.rho
+
+    def observe_energy(self, h):
+        return float(np.trace(self.rho.dot(np.real(h))))
+
+    def check_orthogonality_mps(self):
+        a = self._be.to_numpy(self.mps[0])
+        b = self._be.to_numpy(self.mps[2])
+        k = a.shape[2]
+        return (np.abs(np.einsum('asx,asy->xy', a, a) - np.eye(k)).max() < 1e-12 and
+                np.abs(np.einsum('asx,asy->xy', b, b) - np.eye(k)).max() < 1e-12)
+
+
+class MpsStandardTEBD(MpsOpenBoundaryClass):
+    """imaginary-time TEBD with two-body gates on the CUDA kernels (library/MPSClass.py:1408-1447): evolve_gate_tebd applies the
+    two halves of an SVD-split gate to sites p1 < p2 (growing the bonds in between by the gate rank), truncate_mps_tebd brings
+    the bonds back to chi with SVD-truncating gauge moves (tn_svd_jacobi with k_keep)."""
+
+    def __init__(self, length, d, chi, spin='half', ini_way='r', evolve_way='gate'):
+        MpsOpenBoundaryClass.__init__(self, length, d, chi, spin=spin, way='qr', ini_way=ini_way, operators=None, debug=False,
+                                      is_parallel=False, is_save_op=False, eig_way=0, par_pool=None, is_env_parallel_lmr=False)
+        self.chi = chi
+
+    def evolve_tensor(self, p, gate, enlarge_which_bond):
+        """mps[p] <- gate (d, dd, d) applied on the physical bond, the gate's middle index merged into the right (2) or left (0)
+        virtual bond (library/MPSClass.py:894-907)"""
+        import torch
+        self._ensure_device()
+        be = self._be
+        gate = np.real(np.asarray(gate))
+        d, dd = gate.shape[:2]
+        T = self.mps[p]
+        chi1, _, chi2 = T.shape
+        parts = [be.site_op(T, gate[:, k, :]) for k in range(dd)]      # parts[k][a, s, b] = sum_s' gate[s, k, s'] T[a, s', b]
+        if enlarge_which_bond == 2:
+            self.mps[p] = torch.stack(parts, dim=2).reshape(chi1, d, dd * chi2).contiguous()     # (a, s, k, b)
+            self.virtual_dim[p + 1] = dd * chi2
+        else:
+            self.mps[p] = torch.stack(parts, dim=0).reshape(dd * chi1, d, chi2).contiguous()     # (k, a, s, b)
+            self.virtual_dim[p] = dd * chi1
+        self.orthogonality[p] = 0
+
+    def evolve_gate_tebd(self, p1, p2, gates):
+        import torch
+        if p1 > p2:
+            p1, p2 = p2, p1
+        dd = np.asarray(gates[0]).shape[1]
+        self.evolve_tensor(p1, gates[0], 2)
+        for n in range(p1 + 1, p2):   # identity string of dimension dd through the sites in between (:1421-1427)
+            t = self.mps[n]
+            a, d, b = t.shape
+            eye = torch.eye(dd, dtype=t.dtype, device=t.device)
+            self.mps[n] = torch.einsum('kl,asb->kaslb', eye, t).reshape(dd * a, d, dd * b).contiguous()
+            self.virtual_dim[n + 1] = dd * b
+            self.orthogonality[n] = 0
+        self.evolve_tensor(p2, gates[1], 0)
+
+    def truncate_mps_tebd(self, p1, p2):
+        if p1 > p2:
+            p1, p2 = p2, p1
+        c0 = self.center
+        if c0 < p1:
+            self.orthogonalize_mps(p2, p1, normalize=True, is_trun=False)
+            self.orthogonalize_mps(c0, p1, normalize=True, is_trun=False)
+        elif c0 > p2:
+            self.orthogonalize_mps(self.center, p1, normalize=True, is_trun=False)
+        else:
+            self.orthogonalize_mps(p2, p1, normalize=True, is_trun=False)
+        self.orthogonalize_mps(p1, p2, normalize=True, is_trun=True, chi=self.chi)
+        self.center = p2
+
+    def norm_mps(self, if_normalize=False):
+        norm = MpsOpenBoundaryClass.norm_mps(self)
+        if if_normalize and self.center > -0.1:
+            self.mps[self.center] = self.mps[self.center] / norm
+        return norm
+
+    def observe_bond_energy_from_jxyz(self, pos2, jx, jy, jz, tol=1e-20):
+        """eb[n] = jx <sx sx> + jy <sy sy> + jz <sz sz> on the pairs pos2 (library/MPSClass.py:1184-1194).  sy is complex; its
+        correlator is measured through the real ladder operators, sy (x) sy = -(su - sd) (x) (su - sd) / 4."""
+        pos2 = np.asarray(pos2, dtype=int)
+        terms, weight = [], []
+        for n in range(pos2.shape[0]):
+            a, b = sorted((int(pos2[n, 0]), int(pos2[n, 1])))
+            for o1, o2, c in ((1, 1, jx), (3, 3, jz), (4, 4, -jy / 4), (4, 5, jy / 4), (5, 4, jy / 4), (5, 5, -jy / 4)):
+                if abs(c) > tol:
+                    terms.append(((a, o1), (b, o2)))
+                    weight.append((n, c))
+        vals = self._expect(terms)
+        eb = np.zeros((pos2.shape[0], 1))
+        for (n, c), v in zip(weight, vals):
+            eb[n] += c * v
+        return eb

@@ -157,3 +157,39 @@ def physical_dim_from_spin(spin):
 def show_parameters(para):
     from .BasicFunctionsSJR import print_dict
     return print_dict(para, welcome='The parameters are: \n', style_sep=':\n')
+
+
+# ---- infinite DMRG / TEBD parameter dicts of the library generation (library/Parameters.py:334-369, 430-467) ----
+def generate_parameters_infinite_dmrg():
+    para = dict(dmrg_type='mpo', spin='half', jxy=0, jz=1, hx=0.5, hz=0, n_site=2, chi=16, sweep_time=1000, tau=1e-4,
+                eigs_tol=1e-15, break_tol=2e-10, is_symme_env=False, is_real=True, form='center_ort', dt_ob=10,
+                data_path='.\\data_idmrg\\')
+    return make_para_consistent_idmrg(para)
+
+
+def make_para_consistent_idmrg(para):
+    if para['dmrg_type'] not in ('mpo', 'white'):
+        print("Bad para['d,rg_type']. Set to 'white'")
+        para['dmrg_type'] = 'white'
+    if para['dmrg_type'] == 'white':
+        para['is_symme_env'] = True      # 'white' only suits nearest-neighbour chains with mirror-symmetric environments
+    para['model'] = 'heisenberg'
+    para['hamilt_index'] = hm.hamiltonian_indexes(para['model'], (para['jxy'], para['jz'], -para['hx'] / 2, -para['hz'] / 2))
+    para['d'] = physical_dim_from_spin(para['spin'])
+    return para
+
+
+def generate_parameters_standard_tebd(lattice='chain'):
+    para = dict(spin='half', jxy=1, jz=1, hx=0, hz=0, l=12, chi=32, bound_cond='open', tau0=1e-1, dtau=0.1, taut=3, dt_ob=10,
+                iterate_time=5000, lattice=lattice, save_mode='final', if_break=True, break_tol=1e-7, data_path='.\\data_tebd\\')
+    return make_para_consistent_tebd(para)
+
+
+def make_para_consistent_tebd(para):
+    para['positions_h2'] = hm.positions_nearest_neighbor_1d(para['l'], para['bound_cond'])
+    para['num_h2'] = para['positions_h2'].shape[0]
+    para['d'] = physical_dim_from_spin(para['spin'])
+    para['op'] = _six_ops(para['spin'])
+    para['op'].append(-para['hx'] * para['op'][1] - para['hz'] * para['op'][3])
+    para['ob_time'] = int(para['iterate_time'] / para['dt_ob'])
+    return para
