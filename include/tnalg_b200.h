@@ -242,6 +242,21 @@ int tn_svd_jacobi(const double* A /* [dev] */, int m, int n, int k_keep, double*
                   double* Vt /* [dev] */, int* sweeps_out, void* workspace /* [dev] */, size_t workspace_bytes,
                   void* stream);
 
+/* --------------------------------------------------------------------------------------------------
+ * Observables (a10: observation_s1 / observation_s1_s2, MPSClass.py:857-909; observe_magnetization :911, observe_bond_energy :923):
+ * <op(site)> and <op1(site1) op2(site2)>, site1 < site2, on an MPS whose sites < center are left- and sites > center
+ * right-orthonormal.  mps: [host] array of L [dev] tensors, tensor s of shape (dims[s], d, dims[s+1]); operators row-major d x d
+ * [host], one (pair) per term; out: [host] n_terms doubles.  Blocking.  Each term is one chain of tn_env_update transfers and a
+ * trace (the Python layer batches terms that share chain prefixes; this is the per-term form for direct bindings).
+ * -------------------------------------------------------------------------------------------------- */
+size_t tn_expect_workspace_bytes(const int* dims /* [host] L+1 */, int L, int d, int n_terms);
+int tn_expect_1body(const double* const* mps, const int* dims, int L, int d, int center, int n_terms, const int* sites /* [host] */,
+                    const double* ops /* [host] n_terms*d*d */, double* out, void* workspace /* [dev] */, size_t workspace_bytes,
+                    void* stream);
+int tn_expect_2body(const double* const* mps, const int* dims, int L, int d, int center, int n_terms, const int* site1,
+                    const int* site2, const double* ops1, const double* ops2, double* out, void* workspace /* [dev] */,
+                    size_t workspace_bytes, void* stream);
+
 /* Symmetric eigenproblem on the same Jacobi kernels (the north_star's "Jacobi SVD/eigh"): A (n,n) symmetric -> w (n) ascending,
  * V (n,n) row-major with eigenvector j in column j.  The dense local solve of eig_way = 0 (MPSClass.py:792-794). Blocking. */
 size_t tn_eigh_workspace_bytes(int n);

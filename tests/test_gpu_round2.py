@@ -430,3 +430,26 @@ def test_tebd_standard_vs_reference_gpu(be, golden):
     """f3 on the CUDA path: tebd_standard against the reference's evolved state and observables"""
     from tests.test_idmrg_tebd_cpu import check_tebd
     check_tebd(golden, be)
+
+
+def test_expect_c_abi_vs_oracle(be):
+    """a10 through tn_expect_1body / tn_expect_2body against the oracle's transfer chains and against the batched
+    Python path, centre at the left end, in the middle and at the right end"""
+    from tnalg_b200.MPSClass import MpsOpenBoundaryClass
+    L, d, chi = 9, 2, 24
+    ops_ = [np.real(o) if np.abs(np.imag(o)).max() == 0 else o for o in orc.spin_operators('half')]
+    np.random.seed(21)
+    A = MpsOpenBoundaryClass(L, d, chi, operators=ops_)
+    for c in (0, 4, 8):
+        A.correct_orthogonal_center(c)
+        A.mps[c] = A.mps[c] / A.norm_mps()
+        O = orc.OracleMps(L, d, chi, ops_, mps=[be.to_numpy(t) for t in A.mps])
+        O.center = c
+        one = [((i, ops_[3]),) for i in range(L)] + [((2, ops_[1]),), ((7, ops_[4] + ops_[5]),)]
+        two = [((0, ops_[3]), (8, ops_[3])), ((3, ops_[4]), (4, ops_[5])), ((1, ops_[1]), (6, ops_[3])), ((5, ops_[3]), (6, ops_[3]))]
+        got = be.expect_terms(list(A.mps), c, one + two)
+        want = [O.observe_one_body(3, i) for i in range(L)] + [O.observe_one_body(1, 2), O.observe_one_body(4, 7) + O.observe_one_body(5, 7)]
+        want += [O.observe_two_body([3, 3], [0, 8]), O.observe_two_body([4, 5], [3, 4]), O.observe_two_body([1, 3], [1, 6]),
+                 O.observe_two_body([3, 3], [5, 6])]
+        assert np.abs(got - np.real(want)).max() < 1e-12
+        assert np.abs(got[:L] - A.observe_magnetization(3).reshape(-1)).max() < 1e-12

@@ -82,6 +82,11 @@ SIGNATURES = {
     'tn_comm_allreduce_sum': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     'tn_comm_allgather': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     'tn_comm_broadcast_many': (C.c_int, [C.c_void_p, c_void_pp, c_longlong_p, c_int_p, C.c_int, C.c_void_p]),
+    'tn_expect_workspace_bytes': (C.c_size_t, [c_int_p, C.c_int, C.c_int, C.c_int]),
+    'tn_expect_1body': (C.c_int, [c_void_pp, c_int_p, C.c_int, C.c_int, C.c_int, C.c_int, c_int_p, c_double_p, c_double_p, C.c_void_p,
+                                  C.c_size_t, C.c_void_p]),
+    'tn_expect_2body': (C.c_int, [c_void_pp, c_int_p, C.c_int, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_double_p, c_double_p,
+                                  c_double_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'tn_eigh_workspace_bytes': (C.c_size_t, [C.c_int]),
     'tn_eigh_jacobi': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, c_int_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'tn_qr_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),

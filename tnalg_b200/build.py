@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libtnalg_b200.so')
 STAMP = os.path.join(HERE, 'csrc', '.build_stamp')
 SOURCES = ['lib.cu', 'chain_gemm.cu', 'chain_gemm_tma.cu', 'vector_ops.cu', 'effh_plan.cu', 'lanczos.cu', 'jacobi_svd.cu', 'comm.cu',
-           'qr_householder.cu', 'ed_apply.cu', 'jacobi_eigh.cu']
+           'qr_householder.cu', 'ed_apply.cu', 'jacobi_eigh.cu', 'expect.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-cudart', 'shared',
               '-Xcompiler', '-fPIC', '-I', os.path.join(ROOT, 'include'), '-I', CSRC]
 

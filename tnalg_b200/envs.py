@@ -117,6 +117,16 @@ class EnvCache:
         self.rv = length   # right blocks of bonds rv..L are valid
         self.n_bond_moves = 0
         self.merge_crossing = True   # False: one GEMM link per crossing term, the reference's literal '1_0_1' list
+        # operator pairs with ops[s'] == ops[s]^T (S- = (S+)^T): the block of (i, s') is the transpose of the block of (i, s)
+        # -- T^T (E (x) op^T) T = (T^T (E^T (x) op) T)^T and E^T is the partner's block by induction -- so only one of the two
+        # is transferred through a bond move and the other is a transposed copy
+        self.transpose_of = {}
+        ops_ = terms.ops
+        for s2 in range(len(ops_)):
+            for s1 in range(s2):
+                if ops_[s1] is not None and ops_[s2] is not None and ops_[s1].shape == ops_[s2].shape and \
+                        not np.array_equal(ops_[s1], ops_[s1].T) and np.array_equal(ops_[s2], ops_[s1].T):
+                    self.transpose_of.setdefault(s2, s1)
         self.comm = None             # backend communicator when the outgoing operators of a bond move are sharded over ranks
 
     def invalidate_site(self, n):
@@ -158,6 +168,12 @@ class EnvCache:
         comm.broadcast_many(res, [owner[j] for j in range(len(outputs))])
         return res
 
+    def _mirrored(self, live):
+        """{(site, s'): (site, s)} for the live operators whose block is the transpose of another live block"""
+        have = set(live)
+        return {(i, s2): (i, self.transpose_of[s2]) for (i, s2) in live
+                if s2 in self.transpose_of and (i, self.transpose_of[s2]) in have}
+
     def _lincomb(self, block, pairs):
         xs = [block['O'][key] for _, key in pairs]
         cs = [c for c, _ in pairs]
@@ -180,7 +196,11 @@ class EnvCache:
         if links:
             outputs.append(links)
             keys.append('H')
-        for key in t.open_left(p + 1):
+        live = t.open_left(p + 1)
+        mirrored = self._mirrored(live)
+        for key in live:
+            if key in mirrored:
+                continue
             i, s = key
             outputs.append([(None, t.ops[s])] if i == p else [(cur['O'][key], None)])
             keys.append(key)
@@ -192,6 +212,8 @@ class EnvCache:
                     new['H'] = mat
                 else:
                     new['O'][key] = mat
+        for key, partner in mirrored.items():
+            new['O'][key] = new['O'][partner].t().contiguous()
         self.left[p + 1] = new
         self.n_bond_moves += 1
 
@@ -210,7 +232,11 @@ class EnvCache:
         if links:
             outputs.append(links)
             keys.append('H')
-        for key in t.open_right(p):
+        live = t.open_right(p)
+        mirrored = self._mirrored(live)
+        for key in live:
+            if key in mirrored:
+                continue
             j, s = key
             outputs.append([(None, t.ops[s])] if j == p else [(cur['O'][key], None)])
             keys.append(key)
@@ -222,6 +248,8 @@ class EnvCache:
                     new['H'] = mat
                 else:
                     new['O'][key] = mat
+        for key, partner in mirrored.items():
+            new['O'][key] = new['O'][partner].t().contiguous()
         self.right[p] = new
         self.n_bond_moves += 1
 

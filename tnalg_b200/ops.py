@@ -477,6 +477,34 @@ class CudaBackend:
         L.check(self.lib.tn_eigh_jacobi(_ptr(A), n, _ptr(w), _ptr(V), C.byref(sweeps), _ptr(ws), ws.numel(), self.stream()))
         return w, V
 
+    # ---- a10 through the C ABI: per-term chains (the batched, prefix-sharing form is envs.expect_products) ----
+    def expect_terms(self, mps, center, terms):
+        """terms: list of ((site, op (d,d) array),) or ((site1, op1), (site2, op2)) -> numpy array of expectation values
+        (tn_expect_1body / tn_expect_2body)"""
+        Ls, d = len(mps), mps[0].shape[1]
+        ts = [t.contiguous() for t in mps]
+        dims = (C.c_int * (Ls + 1))(*([ts[0].shape[0]] + [t.shape[2] for t in ts]))
+        ptrs = (C.c_void_p * Ls)(*[t.data_ptr() for t in ts])
+        out = np.zeros(len(terms))
+        for nbody in (1, 2):
+            idx = [i for i, tm in enumerate(terms) if len(tm) == nbody]
+            if not idx:
+                continue
+            n = len(idx)
+            ws = self.workspace('expect', self.lib.tn_expect_workspace_bytes(dims, Ls, d, n))
+            res = (C.c_double * n)()
+            if nbody == 1:
+                st = self.lib.tn_expect_1body(ptrs, dims, Ls, d, int(center), n, (C.c_int * n)(*[int(terms[i][0][0]) for i in idx]),
+                                              _op_array([terms[i][0][1] for i in idx], d), res, _ptr(ws), ws.numel(), self.stream())
+            else:
+                st = self.lib.tn_expect_2body(ptrs, dims, Ls, d, int(center), n, (C.c_int * n)(*[int(terms[i][0][0]) for i in idx]),
+                                              (C.c_int * n)(*[int(terms[i][1][0]) for i in idx]),
+                                              _op_array([terms[i][0][1] for i in idx], d), _op_array([terms[i][1][1] for i in idx], d),
+                                              res, _ptr(ws), ws.numel(), self.stream())
+            L.check(st)
+            out[idx] = np.array(res[:])
+        return out
+
     # ---- (f)4: exact diagonalisation on the full d^L space ----
     def _ed_args(self, couplings, hamilts, d):
         couplings = np.asarray(couplings, dtype=int).reshape(-1, 3)
