@@ -557,7 +557,7 @@ def run_ours(args, para, workload):
         if world == 1:
             for name in ('heis_chain100_chi256', 'xxz_chain200_chi512'):
                 other[name] = quick_workload(torch, dist, name, world, dev, warmup=1, steps=1)
-        elif world == 8 and args.with_cfg5:
+        elif world == 8 and not args.no_cfg5:
             A.clean_to_save()
             del A
             torch.cuda.empty_cache()
@@ -634,7 +634,7 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-e2e', action='store_true', help='skip the e2e leg (profiling runs)')
     ap.add_argument('--no-other', action='store_true', help='skip the other_workloads block (chi=256 / chi=512 chains at N=1)')
-    ap.add_argument('--with-cfg5', action='store_true', help='N=8: add one sweep of the 8x8 chi=2048 workload to other_workloads')
+    ap.add_argument('--no-cfg5', action='store_true', help='N=8: skip the 8x8 chi=2048 workload (BASELINE configs[4]) in other_workloads')
     ap.add_argument('--shard', default='', choices=['', 'rows', 'terms'], help="multi-GPU decomposition (default: 'rows')")
     args = ap.parse_args()
     if args.impl == 'reference':
