@@ -245,18 +245,7 @@ __global__ void __launch_bounds__(kFusedThreads) lanczos_orth_fused_kernel(doubl
   double* p1 = partial;
   double* p2 = partial + (long long)nb * (kMaxNcv + 1);
   double* p3 = p2 + (long long)nb * (kMaxNcv + 1);
-
-  dots(p1);
-  grid.sync();
-  gather(p1);
-  const double h_j = hs[j];
-  update();
-  dots(p2);
-  grid.sync();
-  gather(p2);
-  const double h2_j = hs[j];
-  update();
-  {
+  auto sumsq = [&](double* out) {  // out[b] = sum of ws^2 over this CTA's slice
     double acc = 0.0;
     for (int e = tid; e < len; e += kFusedThreads) acc += ws[e] * ws[e];
     acc = warp_sum_l(acc);
@@ -266,24 +255,44 @@ __global__ void __launch_bounds__(kFusedThreads) lanczos_orth_fused_kernel(doubl
       double s = 0.0;
 #pragma unroll
       for (int k = 0; k < kFusedThreads / 32; ++k) s += red[k];
-      p3[b] = s;
+      out[b] = s;
     }
-  }
+  };
+
+  dots(p1);
   grid.sync();
-  double nrm2 = 0.0;
-  for (int c = lane; c < nb; c += 32) nrm2 += p3[c];
-  nrm2 = warp_sum_l(nrm2);  // every warp of every CTA computes the same value
-  // bookkeeping, identical in every thread of every CTA (reads are of values written before this launch)
+  gather(p1);
+  const double h_j = hs[j];
+  update();
+  dots(p2);
+  sumsq(p3);   // |w'|^2 after the first pass, in the same grid phase as the second-pass coefficients
+  grid.sync();
+  gather(p2);
+  const double h2_j = hs[j];
+  double w1 = 0.0;
+  for (int c = lane; c < nb; c += 32) w1 += p3[c];
+  w1 = warp_sum_l(w1);  // every warp of every CTA computes the same value
+  double s2 = 0.0;
+  for (int i = 0; i < nvec; ++i) s2 += hs[i] * hs[i];
+  update();
+  // |w''|^2 = |w'|^2 - sum h2_i^2 (Pythagoras): accurate while the second pass removes little; if it removed more than half of
+  // |w'|^2 the vector is numerically inside span(V) and the step is a breakdown (the DGKS rule ARPACK applies after its second
+  // pass).  Two grid-wide barriers per step instead of four.
+  double nrm2 = w1 - s2;
+  const bool inside = !(nrm2 > 0.5 * w1);
+  if (nrm2 < 0.0) nrm2 = 0.0;
+  // bookkeeping, identical in every thread of every CTA.  beta[j-1] was written by an earlier launch; `breakdown` may be
+  // rewritten by CTA 0 below while other CTAs still read it, which is benign: it only ever flips 0 -> 1 in a step whose own
+  // test (`inside` / tiny beta, the same data in every CTA) says "broken" as well.
   const double a = h_j + h2_j;
   const double bj = sqrt(nrm2);
   double scale = fabs(a);
   if (j > 0) scale = fmax(scale, fabs(st->beta[j - 1]));
   scale = fmax(scale, 1e-300);
-  const int was_broken = st->breakdown;
-  const bool broken = was_broken || bj <= 1e-14 * scale;
+  const int was_broken = *((volatile int*)&st->breakdown);
+  const bool broken = was_broken || inside || bj <= 1e-14 * scale;
   const double inv = broken ? 0.0 : 1.0 / bj;
   for (int e = tid; e < len; e += kFusedThreads) w[e] = ws[e] * inv;
-  grid.sync();  // every CTA has read st->breakdown / beta[j-1] before CTA 0 updates the state
   if (b == 0 && tid == 0) {
     st->alpha[j] = a;
     st->beta[j] = bj;

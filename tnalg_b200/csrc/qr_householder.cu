@@ -79,11 +79,6 @@ __device__ __forceinline__ void st_async_q(double* local_addr, double v, uint64_
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(ra), "d"(v), "r"(rb) : "memory");
 }
 
-__device__ __forceinline__ double warp_sum_q(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 }  // namespace
 
 // W: work matrix (m x n, leading dimension ld); panel = columns [j0, j0 + nbp), rows [j0, m).
