@@ -8,6 +8,7 @@
 // alpha/beta, the projected tridiagonal eigenproblem, the Ritz selection and the convergence flag live in a small
 // device struct; the host only enqueues kernels and reads one 64-byte status record per restart cycle.
 #include <cmath>
+#include <cstdint>
 #include <cstdlib>
 #include <vector>
 
@@ -180,7 +181,7 @@ __device__ __forceinline__ double warp_sum_l(double v) {
 
 __global__ void __launch_bounds__(kFusedThreads) lanczos_orth_fused_kernel(double* __restrict__ V, long long ldv, int j, long long n,
                                                                            LanczosState* st, double* __restrict__ partial,
-                                                                           int slice_cap, int cache_v) {
+                                                                           int slice_cap, int cache_v, int bulk) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) double dyn[];
   double* ws = dyn;              // this CTA's slice of w (slice_cap doubles)
@@ -189,16 +190,46 @@ __global__ void __launch_bounds__(kFusedThreads) lanczos_orth_fused_kernel(doubl
   __shared__ double red[kFusedThreads / 32];
   const int nb = gridDim.x, b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nvec = j + 1;
-  const long long chunk = (n + nb - 1) / nb;
+  // slices of slice_cap elements (even): CTA b owns [b * slice_cap, ...); with bulk staging the slices are 16-byte granular
+  const long long chunk = bulk ? (long long)slice_cap : (n + nb - 1) / nb;
   const long long e0 = min((long long)b * chunk, n);
   const int len = (int)(min(e0 + chunk, n) - e0);
   double* w = V + (long long)(j + 1) * ldv + e0;
   const double* Vg = V + e0;
-  for (int e = tid; e < len; e += kFusedThreads) ws[e] = w[e];
-  if (cache_v) {  // one coalesced pass over the basis slice; all later phases run out of shared memory
-    for (int i = 0; i < nvec; ++i) {
-      const double* v = Vg + (long long)i * ldv;
-      for (int e = tid; e < len; e += kFusedThreads) vs[i * slice_cap + e] = v[e];
+  if (bulk) {
+    // the CTA's slice of w and of v_0..v_j: one 1-D bulk copy per vector (cp.async.bulk, UBLKCP), all in flight at once and
+    // signalled on one mbarrier -- a plain load/store loop serialises ~20 L2 round trips here (40 % of the kernel was spent
+    // waiting on them, profiles/r02_small_chi.md)
+    __shared__ uint64_t bar;
+    const unsigned bytes = (unsigned)(len * sizeof(double));   // len is even: multiple of 16
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&bar)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0 && len > 0) {
+      const unsigned bar_a = (unsigned)__cvta_generic_to_shared(&bar);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes * (unsigned)(1 + (cache_v ? nvec : 0))) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       (unsigned)__cvta_generic_to_shared(ws)), "l"(w), "r"(bytes), "r"(bar_a) : "memory");
+      if (cache_v)
+        for (int i = 0; i < nvec; ++i)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           (unsigned)__cvta_generic_to_shared(vs + (size_t)i * slice_cap)), "l"(Vg + (long long)i * ldv), "r"(bytes), "r"(bar_a) : "memory");
+    }
+    if (len > 0) {
+      asm volatile(
+          "{\n.reg .pred p;\nLZ_WAIT_%=:\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+          "@!p bra LZ_WAIT_%=;\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(&bar)) : "memory");
+    }
+  } else {
+    for (int e = tid; e < len; e += kFusedThreads) ws[e] = w[e];
+    if (cache_v) {  // one coalesced pass over the basis slice; all later phases run out of shared memory
+      for (int i = 0; i < nvec; ++i) {
+        const double* v = Vg + (long long)i * ldv;
+        for (int e = tid; e < len; e += kFusedThreads) vs[i * slice_cap + e] = v[e];
+      }
     }
   }
   __syncthreads();
@@ -409,7 +440,7 @@ static int lanczos_core(LanczosOp& op, long long n, long long n_loc, long long o
   TN_CHECK(launch_scale_dev(vec(0), &st->inv_beta, n_loc, stream));
 
   // fused cooperative re-orthogonalisation when the vectors are L2 resident and a slice fits the shared-memory buffer
-  int fused_grid = 0, fused_slice = 0, fused_cache = 0;
+  int fused_grid = 0, fused_slice = 0, fused_cache = 0, fused_bulk = 0;
   size_t fused_smem = 0;
   if (!sliced && n <= kFusedMaxN && !getenv("TNALG_NO_FUSED_ORTH")) {
     const int sms = sm_count();
@@ -419,6 +450,8 @@ static int lanczos_core(LanczosOp& op, long long n, long long n_loc, long long o
     const size_t smem1 = sizeof(double) * (size_t)slice1 * (size_t)(m + 2);
     if (smem1 <= 200 * 1024) {
       fused_grid = grid1; fused_slice = slice1; fused_cache = 1; fused_smem = smem1;
+      // bulk-copy staging needs 16-byte granular slices: even n (ldv is even, the workspace 256-byte aligned)
+      fused_bulk = (n % 2 == 0 && (reinterpret_cast<uintptr_t>(V) & 15) == 0 && !getenv("TNALG_NO_BULK_ORTH")) ? 1 : 0;
     }  // larger vectors: the streaming kernels (more CTAs in flight) are faster than an uncached fused pass
     if (fused_grid > 0) {
       static size_t configured = 0;
@@ -456,8 +489,9 @@ static int lanczos_core(LanczosOp& op, long long n, long long n_loc, long long o
         // one cooperative launch: CGS2, norm, scale and the alpha/beta bookkeeping of step j
         long long ldv_arg = ldv, n_arg = n;
         int j_arg = j;
+        int bulk_arg = fused_bulk;
         void* args[] = {(void*)&V, (void*)&ldv_arg, (void*)&j_arg, (void*)&n_arg, (void*)&st, (void*)&partial,
-                        (void*)&fused_slice, (void*)&fused_cache};
+                        (void*)&fused_slice, (void*)&fused_cache, (void*)&bulk_arg};
         TN_CUDA(cudaLaunchCooperativeKernel((const void*)lanczos_orth_fused_kernel, dim3(fused_grid), dim3(kFusedThreads), args,
                                             fused_smem, stream));
         TN_LAUNCHED();
