@@ -18,6 +18,8 @@ from tests.cpu_backend import CpuBackend, install as cpu_backend_install
 from tnalg_b200 import ops
 cpu_backend_install(CpuBackend())                     # host-logic test: no GPU in this container
 import MPSClass, DMRG_anyH, Parameters as Pm, BasicFunctionsSJR as Bf, HamiltonianModule, TensorBasicModule, Eigs_Module_sjr
+import TEBDalgo, EDspinClass                          # library/ generation entry points on the same kernels
+assert callable(TEBDalgo.tebd_standard) and callable(DMRG_anyH.dmrg_infinite_size) and hasattr(MPSClass, 'MpsInfinite')
 assert MPSClass.MpsOpenBoundaryClass.__module__ == 'MPSClass'
 para = Pm.generate_parameters_dmrg('chain')          # reference testDMRG.py:1-8
 para.update(l=6, chi=8, sweep_time=4, dt_ob=2)

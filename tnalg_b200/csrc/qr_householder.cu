@@ -88,9 +88,12 @@ __device__ __forceinline__ void st_async_q(double* local_addr, double v, uint64_
 // the panel spans several CTAs -- per column).
 #ifdef TN_QR_TIMING
 __device__ long long g_qr_clk[8];
+__device__ long long g_qr_aclk[8];   // apply kernel: phases 0..6, [7] = launches
+#define QR_ACLK(slot) do { if (threadIdx.x == 0 && blockIdx.x == 0) { long long now_ = clock64(); g_qr_aclk[slot] += now_ - aclk_; aclk_ = now_; } } while (0)
 #define QR_CLK(slot) do { if (threadIdx.x == 0 && blockIdx.x == 0) { long long now_ = clock64(); g_qr_clk[slot] += now_ - tclk_; tclk_ = now_; } } while (0)
 #else
 #define QR_CLK(slot) do { } while (0)
+#define QR_ACLK(slot) do { } while (0)
 #endif
 
 template <int RPT, bool KEEP, int WARPS>
@@ -203,9 +206,22 @@ __global__ void __launch_bounds__(WARPS * 32, 1) qr_panel_kernel(double* __restr
         }
       }
       mbar_wait_q(&xbar[par], (unsigned)((j >> 1) & 1));
-      for (int s = 0; s < C; ++s) {
-        gk += slots[par][s][lane];
-        gj += slots[par][s][j];
+      {
+        double pk[QMAXC], pj[QMAXC];  // contributions of the C CTAs, summed as a tree (FP64 adds are ~38 cycles deep)
+#pragma unroll
+        for (int s = 0; s < QMAXC; ++s) {
+          pk[s] = s < C ? slots[par][s][lane] : 0.0;
+          pj[s] = s < C ? slots[par][s][j] : 0.0;
+        }
+#pragma unroll
+        for (int st = 1; st < QMAXC; st *= 2)
+#pragma unroll
+          for (int s = 0; s + st < QMAXC; s += 2 * st) {
+            pk[s] += pk[s + st];
+            pj[s] += pj[s + st];
+          }
+        gk = pk[0];
+        gj = pj[0];
       }
       rjk = slots[par][0][QNB + lane];
       alpha = slots[par][0][QNB + j];
@@ -318,18 +334,24 @@ __global__ void __launch_bounds__(WARPS * 32, 1) qr_panel_kernel(double* __restr
 }
 
 #ifdef TN_QR_TIMING
-extern "C" int tn_qr_debug_clocks(long long* out8, int reset) {
+extern "C" int tn_qr_debug_clocks(long long* out8, int reset) {   // out8: 16 values, panel phases then apply phases
   long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (out8) {
     if (cudaMemcpyFromSymbol(h, g_qr_clk, sizeof(h)) != cudaSuccess) return -2;
     for (int i = 0; i < 8; ++i) out8[i] = h[i];
+    if (cudaMemcpyFromSymbol(h, g_qr_aclk, sizeof(h)) != cudaSuccess) return -2;
+    for (int i = 0; i < 8; ++i) out8[8 + i] = h[i];
   }
   if (reset) {
     long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (cudaMemcpyToSymbol(g_qr_clk, z, sizeof(z)) != cudaSuccess) return -2;
+    if (cudaMemcpyToSymbol(g_qr_aclk, z, sizeof(z)) != cudaSuccess) return -2;
   }
   return 0;
 }
+static int qr_debug_skip() { const char* e = getenv("TNALG_QR_DEBUG_SKIP"); return e ? atoi(e) : 0; }
+#else
+static int qr_debug_skip() { return 0; }
 #endif
 
 // Cm[j0:m, c_begin:c_end] <- (1 - V op(T) V^T) Cm[j0:m, c_begin:c_end];  transT != 0: op(T) = T^T.
@@ -345,6 +367,10 @@ extern "C" int tn_qr_debug_clocks(long long* out8, int reset) {
 __global__ void __launch_bounds__(ATHREADS, 1) qr_apply_kernel(const double* __restrict__ Wv, int ldv, int m, int j0, int nbp,
                                                                const double* __restrict__ T, int transT, double* __restrict__ Cm,
                                                                int ldc, int c_begin, int c_end, int RB, int vp, int cp) {
+#ifdef TN_QR_TIMING
+  long long aclk_ = clock64();
+  if (threadIdx.x == 0 && blockIdx.x == 0) g_qr_aclk[7] += 1;
+#endif
   cg::cluster_group cluster = cg::this_cluster();
   const int CR = (int)cluster.num_blocks(), cr = (int)cluster.block_rank();
   extern __shared__ __align__(16) double sm_apply[];
@@ -389,8 +415,10 @@ __global__ void __launch_bounds__(ATHREADS, 1) qr_apply_kernel(const double* __r
       }
     }
   }
+  QR_ACLK(0);
   if (CR > 1) cluster_barrier();  // peers are resident (remote writes below); doubles as the CTA barrier
   else __syncthreads();
+  QR_ACLK(1);
 
   // ---- phase 1: tile (mt, 2 n-tiles) of W = V^T C over all rows of this CTA; 4 interleaved accumulators per tile ----
   {
@@ -435,7 +463,9 @@ __global__ void __launch_bounds__(ATHREADS, 1) qr_apply_kernel(const double* __r
       }
     }
   }
+  QR_ACLK(2);
   if (CR > 1) cluster_barrier(); else __syncthreads();
+  QR_ACLK(3);
   for (int e = tid; e < WSZ; e += ATHREADS) {  // total over the CTAs in rank order
     double s = 0.0;
     for (int src = 0; src < CR; ++src) s += Wex[src * WSZ + e];
@@ -451,6 +481,7 @@ __global__ void __launch_bounds__(ATHREADS, 1) qr_apply_kernel(const double* __r
     W2[e] = -((s4[0] + s4[1]) + (s4[2] + s4[3]));
   }
   __syncthreads();
+  QR_ACLK(4);
   // ---- phase 2: C += V W2 on this CTA's rows (M = rows, N = 32, K = 32; warps take groups of 8 rows) ----
   const int n_oct = (nrows + 7) / 8;
   constexpr int UO = 2;  // row groups per batch
@@ -495,7 +526,9 @@ __global__ void __launch_bounds__(ATHREADS, 1) qr_apply_kernel(const double* __r
       }
     }
   }
+  QR_ACLK(5);
   if (CR > 1) cluster_barrier();  // no CTA exits while a peer may still write its exchange slots
+  QR_ACLK(6);
 }
 
 // out (rows x cols, ld ldo) = in^T or in;  tiled through shared memory
@@ -672,11 +705,12 @@ extern "C" int tn_qr_householder(const double* A, int m, int n, int trans_in, do
   TN_LAUNCHED();
   // right-looking with look-ahead: after panel p, its reflectors are applied to the columns of panel p+1 first; the update of the
   // remaining columns then runs on a side stream while panel p+1 (latency bound, a handful of SMs) is factored on the main stream
+  const int dbg_skip = qr_debug_skip();   // timing builds only: 1 = no Q formation, 2 = no wide trailing updates, 4 = no look-ahead updates, 8 = no panels
   QrSide* side = (panels > 2 && n > 4 * QNB && !getenv("TNALG_QR_NO_LOOKAHEAD")) ? qr_side() : nullptr;
   for (int p = 0; p < panels; ++p) {
     const int j0 = p * QNB, nbp = std::min(QNB, k - j0);
     const double* Tp = Tall + (size_t)p * QNB * QNB;
-    TN_CHECK(launch_panel(W, n, m, j0, nbp, tau, Tall + (size_t)p * QNB * QNB, stream));
+    if (!(dbg_skip & 8)) TN_CHECK(launch_panel(W, n, m, j0, nbp, tau, Tall + (size_t)p * QNB * QNB, stream));
     const int next_end = std::min(n, j0 + nbp + QNB);
     if (!side || next_end >= n) {
       if (side && p > 0) TN_CUDA(cudaStreamWaitEvent(stream, side->join, 0));
@@ -685,10 +719,10 @@ extern "C" int tn_qr_householder(const double* A, int m, int n, int trans_in, do
       continue;
     }
     if (p > 0) TN_CUDA(cudaStreamWaitEvent(stream, side->join, 0));   // the previous wide update has reached these columns
-    TN_CHECK(launch_apply(W, n, m, j0, nbp, Tp, 1, W, n, j0 + nbp, next_end, stream));
+    if (!(dbg_skip & 4)) TN_CHECK(launch_apply(W, n, m, j0, nbp, Tp, 1, W, n, j0 + nbp, next_end, stream));
     TN_CUDA(cudaEventRecord(side->fork, stream));
     TN_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
-    TN_CHECK(launch_apply(W, n, m, j0, nbp, Tp, 1, W, n, next_end, n, side->s));
+    if (!(dbg_skip & 2)) TN_CHECK(launch_apply(W, n, m, j0, nbp, Tp, 1, W, n, next_end, n, side->s));
     TN_CUDA(cudaEventRecord(side->join, side->s));
     if (p == panels - 1) TN_CUDA(cudaStreamWaitEvent(stream, side->join, 0));   // wide matrix: the last update still runs on the side stream
   }
@@ -697,7 +731,7 @@ extern "C" int tn_qr_householder(const double* A, int m, int n, int trans_in, do
   double* Qdst = trans_q ? Qw : Q;
   qr_eye_kernel<<<grid_for((long long)m * k), 256, 0, stream>>>(Qdst, m, k);
   TN_LAUNCHED();
-  for (int p = panels - 1; p >= 0; --p) {
+  for (int p = panels - 1; p >= 0 && !(dbg_skip & 1); --p) {
     const int j0 = p * QNB, nbp = std::min(QNB, k - j0);
     TN_CHECK(launch_apply(W, n, m, j0, nbp, Tall + (size_t)p * QNB * QNB, 0, Qdst, k, j0, k, stream));
   }

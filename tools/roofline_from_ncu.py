@@ -6,8 +6,8 @@ import json
 import sys
 
 KEYS = [('gpu__time_duration.sum', 'us', 1e-3), ('dram__bytes_read.sum', 'MB read', 1e-6), ('dram__bytes_write.sum', 'MB written', 1e-6),
-        ('sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active', 'FP64 pipe %', 1.0),
-        ('sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active', 'FP64 pipe active %', 1.0),
+        ('sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active', 'DMMA pipe %', 1.0),
+        ('sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active', 'FP64 (DFMA) pipe %', 1.0),
         ('smsp__issue_active.avg.pct_of_peak_sustained_active', 'issue active %', 1.0),
         ('sm__warps_active.avg.pct_of_peak_sustained_active', 'warps active %', 1.0),
         ('launch__registers_per_thread', 'regs', 1.0), ('launch__grid_size', 'grid', 1.0), ('launch__cluster_dim_x', 'cluster', 1.0)]
@@ -38,8 +38,8 @@ for path in sys.argv[1:]:
         for k, lab, sc in cols:
             v = num(r[hdr.index(k)])
             u = units[hdr.index(k)]
-            if v is not None and k.startswith('gpu__time') and u == 'ns':
-                v = v * 1e-3
+            if v is not None and k.startswith('gpu__time'):
+                v = v * {'ns': 1e-3, 'nsecond': 1e-3, 'us': 1.0, 'usecond': 1.0, 'ms': 1e3, 'msecond': 1e3, 's': 1e6, 'second': 1e6}.get(u, 1.0)
             elif v is not None and k.startswith('dram__bytes'):
                 v = v * {'byte': 1e-6, 'Kbyte': 1e-3, 'Mbyte': 1.0, 'Gbyte': 1e3}.get(u, 1e-6)
                 tot += v
