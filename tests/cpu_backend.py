@@ -149,6 +149,9 @@ class CpuBackend:
     def to_numpy(self, t):
         return t.detach().numpy().copy()
 
+    def to_numpy_many(self, tensors):
+        return [self.to_numpy(t) for t in tensors]
+
     def empty(self, *shape):
         return torch.empty(*shape, dtype=torch.float64)
 

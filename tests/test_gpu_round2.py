@@ -265,6 +265,13 @@ def test_observables_chi512_vs_oracle(be):
     corr = A.observe_correlators_from_middle(3, 3)
     ref = O.observe_correlators_from_middle(3, 3)
     assert np.abs(corr - ref).max() < 1e-8
+    # the one-pass form of the sweep driver, with a (S+ S-) / (S- S+) pair that is contracted once
+    index2b = np.array([[9, 10, 4, 5], [9, 10, 5, 4], [10, 11, 3, 3], [3, 18, 3, 3], [2, 7, 4, 5], [2, 7, 5, 4]])
+    coeff2b = np.array([0.5, 0.5, 1.0, 0.25, 0.5, 0.5])
+    eb2, (mx2, mz2) = A.observe_bond_energy_and_magnetization(index2b, coeff2b, (1, 3))
+    for r, c, got in zip(index2b, coeff2b, eb2.reshape(-1)):
+        assert abs(got - c * O.observe_two_body([r[2], r[3]], [r[0], r[1]])) < 1e-8
+    assert np.abs(mx2.reshape(-1) - mx).max() < 1e-12 and np.abs(mz2.reshape(-1) - mz).max() < 1e-12
 
 
 @pytest.mark.parametrize('world', [2, 3, 8])

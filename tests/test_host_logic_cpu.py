@@ -101,6 +101,9 @@ def test_observables_vs_reference(golden, cpu_be):
         A.correct_orthogonal_center(c)
         assert np.abs(A.observe_magnetization(3) - g['ob_mz']).max() < 1e-12
         assert np.abs(A.observe_bond_energy(g['index2'], g['coeff2']) - g['ob_eb_full']).max() < 1e-12
+        # the one-pass form the sweep driver uses (shared density chain, S+S- / S-S+ contracted once)
+        eb, (mx, mz) = A.observe_bond_energy_and_magnetization(g['index2'], g['coeff2'], (1, 3))
+        assert np.abs(eb - g['ob_eb_full']).max() < 1e-12 and np.abs(mx - g['ob_mx']).max() < 1e-12 and np.abs(mz - g['ob_mz']).max() < 1e-12
 
 
 @pytest.mark.parametrize('case', ['e2e_chain12', 'e2e_xxz10', 'e2e_j1j2_4x2', 'e2e_spin1_chain8', 'e2e_longrange8', 'e2e_square3x2', 'e2e_periodic8'])

@@ -26,9 +26,7 @@ def sweep_once(A, para):
 
 
 def observe(A, para, ob):
-    ob['eb_full'] = A.observe_bond_energy(para['index2'], para['coeff2'])
-    ob['mx'] = A.observe_magnetization(1)
-    ob['mz'] = A.observe_magnetization(3)
+    ob['eb_full'], (ob['mx'], ob['mz']) = A.observe_bond_energy_and_magnetization(para['index2'], para['coeff2'], (1, 3))
     ob['e_per_site'] = (sum(ob['eb_full']) - para['hx'] * sum(ob['mx']) - para['hz'] * sum(ob['mz'])) / A.length
     return ob
 

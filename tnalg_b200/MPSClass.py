@@ -545,6 +545,19 @@ class MpsOpenBoundaryClass(MpsBasic):
         vals = self._expect(terms)
         return (np.asarray(coeff2, dtype=float).reshape(-1) * vals).reshape(-1, 1)
 
+    def observe_bond_energy_and_magnetization(self, index2, coeff2, sns=(1, 3)):
+        """observe_bond_energy + observe_magnetization(sn) for sn in sns in ONE pass over the chain (the density chain from the
+        orthogonality centre and the operator-carrying environments are shared): what DMRG_anyH.py:57-63 evaluates after a sweep"""
+        index2 = np.asarray(index2, dtype=int)
+        terms = [tuple(sorted(((int(r[0]), int(r[2])), (int(r[1]), int(r[3]))))) for r in index2]
+        nb = len(terms)
+        for sn in sns:
+            terms += [((i, int(sn)),) for i in range(self.length)]
+        vals = self._expect(terms)
+        eb = (np.asarray(coeff2, dtype=float).reshape(-1) * vals[:nb]).reshape(-1, 1)
+        mags = [vals[nb + k * self.length: nb + (k + 1) * self.length].reshape(-1, 1) for k in range(len(sns))]
+        return eb, mags
+
     def observe_correlators_from_middle(self, op1, op2, ob_len=None):
         if ob_len is None:
             ob_len = self.length
@@ -671,7 +684,12 @@ class MpsOpenBoundaryClass(MpsBasic):
 
     def clean_to_save(self):
         """drop caches and bring the tensors to the host as numpy arrays (MPSClass.py:1090-1098)"""
-        self.mps = [self._be.to_numpy(t) if hasattr(t, 'data_ptr') else np.asarray(t) for t in self.mps]
+        on_dev = [i for i, t in enumerate(self.mps) if hasattr(t, 'data_ptr')]
+        mps = [t if hasattr(t, 'data_ptr') else np.asarray(t) for t in self.mps]
+        if on_dev:
+            for i, h in zip(on_dev, self._be.to_numpy_many([mps[i] for i in on_dev])):
+                mps[i] = h
+        self.mps = mps
         self.effect_s = {'none': np.zeros(0)}
         self.effect_ss = {'none': np.zeros(0)}
         self.effective_id = {'none': np.zeros(0)}

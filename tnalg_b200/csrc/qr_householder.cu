@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 #include "vector_ops.cuh"
@@ -206,22 +207,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) qr_panel_kernel(double* __restr
         }
       }
       mbar_wait_q(&xbar[par], (unsigned)((j >> 1) & 1));
-      {
-        double pk[QMAXC], pj[QMAXC];  // contributions of the C CTAs, summed as a tree (FP64 adds are ~38 cycles deep)
-#pragma unroll
-        for (int s = 0; s < QMAXC; ++s) {
-          pk[s] = s < C ? slots[par][s][lane] : 0.0;
-          pj[s] = s < C ? slots[par][s][j] : 0.0;
-        }
-#pragma unroll
-        for (int st = 1; st < QMAXC; st *= 2)
-#pragma unroll
-          for (int s = 0; s + st < QMAXC; s += 2 * st) {
-            pk[s] += pk[s + st];
-            pj[s] += pj[s + st];
-          }
-        gk = pk[0];
-        gj = pj[0];
+      for (int s = 0; s < C; ++s) {  // fixed order: identical in every CTA and from run to run
+        gk += slots[par][s][lane];
+        gj += slots[par][s][j];
       }
       rjk = slots[par][0][QNB + lane];
       alpha = slots[par][0][QNB + j];
@@ -568,6 +556,30 @@ __global__ void qr_eye_kernel(double* __restrict__ Q, int m, int k) {
     Q[i] = (i / k == i % k) ? 1.0 : 0.0;
 }
 
+// in place: columns [0, k) of the factored work matrix become the explicit unit-lower-trapezoidal V (zeros above the diagonal, ones on
+// it; a reflector with tau = 0 is the identity and its column is cleared).  R has been extracted before.
+__global__ void qr_make_v_kernel(double* __restrict__ W, int ld, int k, const double* __restrict__ tau) {
+  // only the upper triangle + diagonal of the leading k x k block changes
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)k * k; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / k), c = (int)(i % k);
+    if (c > r) W[(size_t)r * ld + c] = 0.0;
+    else if (c == r) W[(size_t)r * ld + c] = tau[c] != 0.0 ? 1.0 : 0.0;
+  }
+}
+// S = T^-1 = diag(1 / tau) + striu(V^T V), from the partial Gram matrices Gp[s] (K split of the GEMM, summed in order);
+// Tf = 0 except for the diagonal 32 x 32 blocks, which are the panel factors.  Both (kp x kp), identity / zero beyond k.
+__global__ void qr_build_s_kernel(const double* __restrict__ Gp, int n_split, size_t split_stride, double* __restrict__ S,
+                                  double* __restrict__ Tf, const double* __restrict__ Tall, int kp, int k) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)kp * kp; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / kp), c = (int)(i % kp);
+    double g = 0.0;
+    if (c > r && c < k && (r >> 5) != (c >> 5))
+      for (int sidx = 0; sidx < n_split; ++sidx) g += Gp[sidx * split_stride + i];
+    S[i] = g;   // only the blocks above the block diagonal are read
+    Tf[i] = ((r >> 5) == (c >> 5) && c < k && r < k) ? Tall[(size_t)(r >> 5) * QNB * QNB + (r & 31) * QNB + (c & 31)] : 0.0;
+  }
+}
+
 struct QrSide {
   cudaStream_t s = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
@@ -664,6 +676,98 @@ static int launch_apply(const double* Wv, int ldv, int m, int j0, int nbp, const
   return TN_OK;
 }
 
+// ---- Q from the compact-WY form of ALL reflectors:  Q = [1; 0] - V (T V1^T),  T^-1 = diag(1 / tau) + striu(V^T V) ----
+// Applying the panels one after the other to the identity is a chain of min(m,n)/32 latency-bound launches (1.4 ms of the
+// 4.4 ms of a 2048 x 1024 factorisation); here the same product is three large DMMA chain GEMMs plus the inversion of the
+// upper-triangular T^-1 by recursive doubling over its diagonal blocks (the 32 x 32 ones are the panel factors),
+//   [[A, B], [0, D]]^-1 = [[A^-1, -A^-1 B D^-1], [0, D^-1]],   two batched GEMMs per level.
+// All GEMMs run in the deterministic schedule (whole tiles, fixed summation order); the K range of the Gram product is cut
+// into separate outputs that are added in order, so the result is bit-reproducible like the rest of the factorisation.
+constexpr int kQrGemmSlots = 16;   // descriptor chunks in the workspace: 1 Gram + 2 per level (<= 6 levels) + 2
+static int qr_kp(int k) {
+  const int panels = (k + QNB - 1) / QNB;
+  int p2 = 1;
+  while (p2 < panels) p2 *= 2;
+  return p2 * QNB;
+}
+static int qr_gram_split(int m, int k) {
+  const int tiles = ((k + kTileBM - 1) / kTileBM) * ((k + kTileBN - 1) / kTileBN);
+  int ns = 1;
+  while (ns < 4 && tiles * ns * 2 <= 2 * sm_count() && m % (2 * ns * kBK) == 0 && m / (2 * ns) >= 256) ns *= 2;
+  return ns;
+}
+static int qr_fullt_min_panels() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TNALG_QR_WY_MIN_PANELS");
+    v = e ? atoi(e) : 8;
+  }
+  return v;
+}
+static size_t qr_gemm_slot_bytes() { return align_up(tn_chain_gemm_workspace_bytes(32, 32)); }
+
+struct QrGemmCall {
+  std::vector<tn_problem> pr;
+  std::vector<tn_link> ln;
+  void add(const double* A, const double* B, double* Cm, double alpha, int accumulate) {
+    tn_link l = {};
+    l.A = A; l.B = B; l.has_op = 0;
+    tn_problem q = {};
+    q.C = Cm; q.alpha = alpha; q.link_begin = (int)ln.size(); q.link_count = 1; q.accumulate = accumulate;
+    ln.push_back(l);
+    pr.push_back(q);
+  }
+  int run(int mode, int M, int N, int K, int lda, int ldb, int ldc, void* slot, cudaStream_t stream) {
+    if (pr.empty()) return TN_OK;
+    TN_REQUIRE(pr.size() <= 32, "tn_qr: too many blocks in one batched product");
+    return tn_chain_gemm(mode, M, N, K, 1, lda, ldb, ldc, pr.data(), (int)pr.size(), ln.data(), (int)ln.size(), 1, slot,
+                         qr_gemm_slot_bytes(), stream);
+  }
+};
+
+// W: factored work matrix (V below the diagonal of its first k columns, R already extracted), Qdst (m x k) receives Q
+static int form_q_compact_wy(double* W, int ld, int m, int k, const double* tau, const double* Tall, double* Qdst, double* Gp,
+                             double* S, double* Tf, double* Y, char* slots, cudaStream_t stream) {
+  const int kp = qr_kp(k);
+  const int ns = qr_gram_split(m, k);
+  const size_t kk = (size_t)kp * kp;
+  int slot = 0;
+  auto next_slot = [&]() { return static_cast<void*>(slots + (size_t)(slot++) * qr_gemm_slot_bytes()); };
+  qr_make_v_kernel<<<grid_for((long long)k * k), 256, 0, stream>>>(W, ld, k, tau);
+  TN_LAUNCHED();
+  {  // partial Gram matrices over row ranges of V
+    QrGemmCall g;
+    const int rows_per = m / ns;
+    for (int i = 0; i < ns; ++i) g.add(W + (size_t)i * rows_per * ld, W + (size_t)i * rows_per * ld, Gp + i * kk, 1.0, 0);
+    TN_CHECK(g.run(TN_TN, k, k, rows_per, ld, ld, kp, next_slot(), stream));
+  }
+  qr_build_s_kernel<<<grid_for((long long)kk), 256, 0, stream>>>(Gp, ns, kk, S, Tf, Tall, kp, k);
+  TN_LAUNCHED();
+  for (int sz = QNB; sz < kp; sz *= 2) {
+    QrGemmCall y, x;
+    for (int a0 = 0; a0 + sz < k; a0 += 2 * sz) {
+      const int d0 = a0 + sz;
+      y.add(S + (size_t)a0 * kp + d0, Tf + (size_t)d0 * kp + d0, Y + (size_t)a0 * kp + d0, 1.0, 0);       // Y = B D^-1
+      x.add(Tf + (size_t)a0 * kp + a0, Y + (size_t)a0 * kp + d0, Tf + (size_t)a0 * kp + d0, -1.0, 0);     // -A^-1 Y
+    }
+    TN_CHECK(y.run(TN_NN, sz, sz, sz, kp, kp, kp, next_slot(), stream));
+    TN_CHECK(x.run(TN_NN, sz, sz, sz, kp, kp, kp, next_slot(), stream));
+  }
+  {  // Y = T V1^T (k x k), V1 = leading k x k block of V
+    QrGemmCall g;
+    g.add(Tf, W, Y, 1.0, 0);
+    TN_CHECK(g.run(TN_NT, k, k, k, kp, ld, kp, next_slot(), stream));
+  }
+  qr_eye_kernel<<<grid_for((long long)m * k), 256, 0, stream>>>(Qdst, m, k);
+  TN_LAUNCHED();
+  {
+    QrGemmCall g;
+    g.add(W, Y, Qdst, -1.0, 1);
+    TN_CHECK(g.run(TN_NN, m, k, k, ld, kp, k, next_slot(), stream));
+  }
+  return TN_OK;
+}
+
 }  // namespace tn
 
 using namespace tn;
@@ -671,8 +775,13 @@ using namespace tn;
 extern "C" size_t tn_qr_workspace_bytes(int m, int n) {
   const int k = std::min(m, n);
   const size_t panels = (size_t)(k + QNB - 1) / QNB;
+  size_t wy = 0;   // compact-WY formation of Q: partial Gram matrices, S, T, scratch (kp x kp each) + GEMM descriptor chunks
+  if ((int)panels >= qr_fullt_min_panels()) {
+    const size_t kk = (size_t)qr_kp(k) * qr_kp(k);
+    wy = align_up(sizeof(double) * kk * qr_gram_split(m, k)) + 3 * align_up(sizeof(double) * kk) + kQrGemmSlots * qr_gemm_slot_bytes();
+  }
   return align_up(sizeof(double) * (size_t)m * n) + align_up(sizeof(double) * (size_t)m * k) + align_up(sizeof(double) * panels * QNB * QNB) +
-         align_up(sizeof(double) * (size_t)(k + QNB)) + 2 * 256 + 1024;
+         align_up(sizeof(double) * (size_t)(k + QNB)) + 2 * 256 + 1024 + wy;
 }
 
 // trans_in != 0: the input is A^T, stored (n, m) row-major (the right-to-left move factorises the transposed matricisation
@@ -696,6 +805,18 @@ extern "C" int tn_qr_householder(const double* A, int m, int n, int trans_in, do
   double* scale2 = cw.take<double>(2);
   unsigned long long* slot = cw.take<unsigned long long>(1);
   TN_REQUIRE(W && Qw && Tall && tau && scale2 && slot, "tn_qr_householder: workspace carve failed");
+  const bool wy = panels >= qr_fullt_min_panels();
+  double *Gp = nullptr, *Sm = nullptr, *Tf = nullptr, *Ym = nullptr;
+  char* gslots = nullptr;
+  if (wy) {
+    const size_t kk = (size_t)qr_kp(k) * qr_kp(k);
+    Gp = cw.take<double>(kk * qr_gram_split(m, k));
+    Sm = cw.take<double>(kk);
+    Tf = cw.take<double>(kk);
+    Ym = cw.take<double>(kk);
+    gslots = cw.take<char>(kQrGemmSlots * qr_gemm_slot_bytes());
+    TN_REQUIRE(Gp && Sm && Tf && Ym && gslots, "tn_qr_householder: workspace carve failed");
+  }
   const dim3 tb(32, 8);
   // The column norms are formed as plain sums of squares, so the work copy is A scaled by a power of two to max|a_ij| in [1/2, 1)
   // (exact; R is scaled back): un-normalised MPS tensors reach 1e300 on long chains and their squares would overflow
@@ -729,11 +850,15 @@ extern "C" int tn_qr_householder(const double* A, int m, int n, int trans_in, do
   qr_extract_r_kernel<<<grid_for((long long)k * n), 256, 0, stream>>>(W, n, R, k, n, scale2 + 1);
   TN_LAUNCHED();
   double* Qdst = trans_q ? Qw : Q;
-  qr_eye_kernel<<<grid_for((long long)m * k), 256, 0, stream>>>(Qdst, m, k);
-  TN_LAUNCHED();
-  for (int p = panels - 1; p >= 0 && !(dbg_skip & 1); --p) {
-    const int j0 = p * QNB, nbp = std::min(QNB, k - j0);
-    TN_CHECK(launch_apply(W, n, m, j0, nbp, Tall + (size_t)p * QNB * QNB, 0, Qdst, k, j0, k, stream));
+  if (wy) {
+    if (!(dbg_skip & 1)) TN_CHECK(form_q_compact_wy(W, n, m, k, tau, Tall, Qdst, Gp, Sm, Tf, Ym, gslots, stream));
+  } else {
+    qr_eye_kernel<<<grid_for((long long)m * k), 256, 0, stream>>>(Qdst, m, k);
+    TN_LAUNCHED();
+    for (int p = panels - 1; p >= 0 && !(dbg_skip & 1); --p) {
+      const int j0 = p * QNB, nbp = std::min(QNB, k - j0);
+      TN_CHECK(launch_apply(W, n, m, j0, nbp, Tall + (size_t)p * QNB * QNB, 0, Qdst, k, j0, k, stream));
+    }
   }
   if (trans_q) {
     qr_copy_kernel<<<dim3((m + 31) / 32, (k + 31) / 32), tb, 0, stream>>>(Qw, k, Q, m, k, m, 1, nullptr);

@@ -391,17 +391,35 @@ def expect_products(be, mps, center, ops, terms):
     """<prod_k op[s_k](site_k)> for every term in `terms` (list of tuples of (site, op_id), sites strictly increasing
     inside a term) on a centre-orthogonal MPS (sites < center left-, sites > center right-orthonormal).
     a10: observation_s1 / observation_s1_s2 (MPSClass.py:857-909) restated as one left-to-right pass:
-    operator-carrying environments are shared by all terms with the same leading (site, op), the far sides are the
-    identity or a 'density' chain rho from the centre, and every bond is one batched tn_env_update call.
+      * operator-carrying environments are shared by all terms with the same leading (site, op); the far sides are the
+        identity or a 'density' chain rho from the centre; every bond is one batched tn_env_update call;
+      * a term is closed on its last site by the inner product of its environment with the block R(site, op) -- the last
+        operator contracted with the site tensor and whatever lies to its right -- built once per distinct (site, op), so closing
+        costs a dot product instead of a transfer per term;
+      * the state is real, so <A> = <A^T>: a term whose operators are the transposes of another term's (S- S+ vs S+ S-) is not
+        contracted twice.
     Returns a float numpy array of len(terms)."""
     L = len(mps)
     if not terms:
         return np.zeros(0)
-    terms = [tuple((int(s), int(o)) for s, o in term) for term in terms]
-    for term in terms:
+    terms_in = [tuple((int(s), int(o)) for s, o in term) for term in terms]
+    for term in terms_in:
         sites = [s for s, _ in term]
         if sites != sorted(set(sites)) or not (0 <= sites[0] and sites[-1] < L):
             raise ValueError('observable sites must be strictly increasing and inside the chain: %r' % (term,))
+    # transpose partner of every operator that occurs (None: its transpose is not in the operator list)
+    used = sorted({o for term in terms_in for _, o in term})
+    partner = {}
+    for o in used:
+        partner[o] = next((o2 for o2 in range(len(ops)) if ops[o2] is not None and ops[o2].shape == ops[o].shape
+                           and np.array_equal(ops[o2], ops[o].T)), None)
+    canon = []
+    for term in terms_in:
+        if all(partner[o] is not None for _, o in term):
+            canon.append(min(term, tuple((s, partner[o]) for s, o in term)))
+        else:
+            canon.append(term)
+    terms = sorted(set(canon))
     first = min(term[0][0] for term in terms)
     last = max(term[-1][0] for term in terms)
     # right density chain: rhoR[q] closes bond q when every site >= q carries no operator and q <= center
@@ -417,8 +435,27 @@ def expect_products(be, mps, center, ops, terms):
     active = {}
     need_rho_left = any(term[0][0] > center for term in terms)
     for q in range(min(first, center) if need_rho_left else first, last + 1):
+        # ---- close the terms that end on this site against R(q, op) ----
+        closing = [term for term in terms if term[-1][0] == q]
+        if closing:
+            close_ops = sorted({term[-1][1] for term in closing})
+            right = rhoR[q + 1] if q < center else None
+            blocks = dict(zip(close_ops, be.env_update(1, mps[q], [[(right, ops[o])] for o in close_ops])))
+            for term in closing:
+                parent = term[:-1]
+                if parent == ():
+                    env = active.get(()) if q > center else None      # identity unless a density has left the centre
+                    if q > center and env is None:
+                        raise RuntimeError('internal: missing density chain at site %d' % q)
+                else:
+                    env = active[parent]
+                blk = blocks[term[-1][1]]
+                slot_of[term] = len(slots)
+                slots.append(be.trace(blk) if env is None else be.dot(env, blk))
+                if len(slots) >= 2048:
+                    raise RuntimeError('too many observables in one call')
+        # ---- which prefixes must exist on bond q+1 ----
         outputs, keys = [], []
-        # which prefixes must exist on bond q+1
         want = set()
         for term in terms:
             sites = [s for s, _ in term]
@@ -426,7 +463,7 @@ def expect_products(be, mps, center, ops, terms):
                 if q >= center and sites[0] > center:
                     want.add(())      # density still travelling towards the first operator
                 continue
-            if sites[-1] < q:
+            if sites[-1] <= q:
                 continue
             k = sum(1 for s in sites if s <= q)  # operators absorbed up to and including site q
             want.add(term[:k])
@@ -453,17 +490,5 @@ def expect_products(be, mps, center, ops, terms):
             res = be.env_update(0, mps[q], outputs)
             new_active = dict(zip(keys, res))
         active = new_active
-        # close the terms that end on this site
-        for n, term in enumerate(terms):
-            if term[-1][0] == q:
-                env = active[term]
-                if q >= center:
-                    slot = be.trace(env)
-                else:
-                    slot = be.dot(env, rhoR[q + 1])
-                slot_of[n] = len(slots)
-                slots.append(slot)
-                if len(slots) >= 2048:
-                    raise RuntimeError('too many observables in one call')
     vals = be.scalars_to_host(slots)
-    return np.array([vals[slot_of[n]] for n in range(len(terms))])
+    return np.array([vals[slot_of[c]] for c in canon])

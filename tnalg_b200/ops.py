@@ -201,6 +201,17 @@ class CudaBackend:
     def to_numpy(self, t):
         return t.detach().cpu().numpy()
 
+    def to_numpy_many(self, tensors):
+        """device tensors -> numpy arrays through page-locked staging buffers: all copies are queued on the stream and waited for
+        once.  The arrays are views of pinned host memory (torch's caching host allocator recycles it when they are dropped)."""
+        host = []
+        for t in tensors:
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t.detach(), non_blocking=True)
+            host.append(h)
+        torch.cuda.current_stream().synchronize()
+        return [h.numpy() for h in host]
+
     def empty(self, *shape):
         return torch.empty(*shape, dtype=torch.float64, device=self.device)
 
