@@ -472,11 +472,13 @@ def run_ours(args, para, workload):
     be.lib.tn_launch_count_reset()
     comm = be.comm()
     coll0 = comm.collectives() if comm is not None else 0
+    peer0 = comm.peer_collectives() if comm is not None else 0
     r = run_sweeps(torch, dist, A, para, args.steps, world, dev)
     barrier, max_over_ranks = r['barrier'], r['max_over_ranks']
     t_ms, solver_ms, n_mv, f_alg, f_exe = r['t_ms'], r['solver_ms'], r['n_mv'], r['f_alg'], r['f_exe']
     launches = be.launch_count()
     collectives = (comm.collectives() - coll0) if comm is not None else 0
+    peer_collectives = (comm.peer_collectives() - peer0) if comm is not None else 0
     clocks = sampler.stop() if rank == 0 else None
     value = n_mv / (t_ms * 1e-3)
     sharding = A.last_eig.get('sharding', 'none')
@@ -619,6 +621,7 @@ def run_ours(args, para, workload):
                   'algorithmic_tflops_sweep': f_alg / (t_ms * 1e-3) / 1e12, 'algorithmic_tflops_solver': f_alg / (solver_ms * 1e-3) / 1e12,
                   'executed_tflops_solver_per_gpu': f_exe / (solver_ms * 1e-3) / 1e12, 'not_converged': not_conv,
                   'sharding': sharding, 'collectives_per_sweep': collectives / args.steps,
+                  'peer_window_collectives_per_sweep': peer_collectives / args.steps,
                   'phases_ms_per_sweep': {'solver (Lanczos: matvec + collectives + vector ops)': solver_ms / args.steps,
                                           'gauge moves (Householder QR + absorb)': r['gauge_ms'] / args.steps,
                                           'environment updates': r['env_ms'] / args.steps,

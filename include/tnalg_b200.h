@@ -221,6 +221,10 @@ int tn_comm_init(tn_comm** comm, void* nccl_comm /* ncclComm_t */, int rank, int
 int tn_comm_rank(const tn_comm* comm);
 int tn_comm_world(const tn_comm* comm);
 long long tn_comm_collectives(const tn_comm* comm); /* collectives issued so far through this handle */
+/* ... of which ran as kernels storing into the peer window (one IPC-mapped buffer per rank over NVLink: the small all-reduces
+ * and the Krylov-vector all-gathers of the row-sliced Lanczos) instead of NCCL launches; 0 when the box does not allow CUDA IPC
+ * between the ranks or TNALG_NO_PEER is set */
+long long tn_comm_peer_collectives(const tn_comm* comm);
 int tn_comm_destroy(tn_comm* comm);
 int tn_comm_allreduce_sum(tn_comm* comm, double* buf /* [dev] */, long long count, void* stream);
 int tn_comm_allgather(tn_comm* comm, const double* send /* [dev] count_per_rank */, double* recv /* [dev] world*count_per_rank */,

@@ -33,6 +33,21 @@ def main():
     t = torch.full((1000,), float(rank + 1), dtype=torch.float64, device=dev)
     comm.allreduce(t)
     assert float(t[0]) == world * (world + 1) / 2
+    # small all-reduces (<= 64 doubles) go through the peer window when CUDA IPC works between the ranks: many in a row
+    # (the slot ring is reused), interleaved with large NCCL ones
+    base = torch.arange(22, dtype=torch.float64, device=dev)
+    for it in range(40):
+        s = base * (rank + 1) + it
+        comm.allreduce(s)
+        assert torch.equal(s, base * (world * (world + 1) / 2) + it * world), it
+        if it % 13 == 0:
+            big = torch.full((5000,), float(rank), dtype=torch.float64, device=dev)
+            comm.allreduce(big)
+            assert float(big[17]) == world * (world - 1) / 2
+    if rank == 0:
+        print('peer-window collectives: %d of %d' % (comm.peer_collectives(), comm.collectives()), flush=True)
+    if not os.environ.get('TNALG_NO_PEER') and os.environ.get('TNALG_EXPECT_PEER'):
+        assert comm.peer_collectives() >= 40
     bufs = [torch.full((64, 64), float(rank * 10 + j), dtype=torch.float64, device=dev) for j in range(5)]
     comm.broadcast_many(bufs, [j % world for j in range(5)])
     for j in range(5):

@@ -78,6 +78,7 @@ SIGNATURES = {
     'tn_comm_rank': (C.c_int, [C.c_void_p]),
     'tn_comm_world': (C.c_int, [C.c_void_p]),
     'tn_comm_collectives': (C.c_longlong, [C.c_void_p]),
+    'tn_comm_peer_collectives': (C.c_longlong, [C.c_void_p]),
     'tn_comm_destroy': (C.c_int, [C.c_void_p]),
     'tn_comm_allreduce_sum': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     'tn_comm_allgather': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),

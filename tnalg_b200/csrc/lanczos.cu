@@ -366,8 +366,10 @@ struct LanczosOp {
       return TN_OK;
     }
     if (rows) {
-      TN_CHECK(comm_allgather(comm, x_loc, full, n_pad, stream));
-      return tn_effh_matvec(plan, full, y_loc, 0.0, 1.0, stream);
+      // the gathered vector arrives in the library's peer window (plain stores over NVLink) when the box allows it, else in `full`
+      const double* gathered = nullptr;
+      TN_CHECK(comm_allgather_window(comm, x_loc, n_pad, full, &gathered, stream));
+      return tn_effh_matvec(plan, gathered, y_loc, 0.0, 1.0, stream);
     }
     TN_CHECK(tn_effh_matvec(plan, x_loc, y_loc, 0.0, 1.0, stream));
     if (comm) return comm_allreduce_sum(comm, y_loc, n, stream);
@@ -540,8 +542,9 @@ static int lanczos_core(LanczosOp& op, long long n, long long n_loc, long long o
   TN_LAUNCHED();
   TN_CHECK(launch_scale_dev(ytmp, &st->inv_beta, n_loc, stream));
   if (sliced) {  // every rank receives the whole eigenvector (bit-identical on all ranks)
-    TN_CHECK(comm_allgather(comm, ytmp, full, op.n_pad, stream));
-    TN_CUDA(cudaMemcpyAsync(vec_out, full, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
+    const double* gathered = nullptr;
+    TN_CHECK(comm_allgather_window(comm, ytmp, op.n_pad, full, &gathered, stream));
+    TN_CUDA(cudaMemcpyAsync(vec_out, gathered, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
   } else {
     TN_CUDA(cudaMemcpyAsync(vec_out, ytmp, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
   }

@@ -122,6 +122,10 @@ class Comm:
     def collectives(self):
         return int(self._be.lib.tn_comm_collectives(self._handle))
 
+    def peer_collectives(self):
+        """collectives that ran as stores into the NVLink peer window instead of NCCL launches"""
+        return int(self._be.lib.tn_comm_peer_collectives(self._handle))
+
     def destroy(self):
         if self._handle is not None:
             self._be.lib.tn_comm_destroy(self._handle)
