@@ -105,8 +105,22 @@ def main():
             e_all = [None] * world
             dist.all_gather_object(e_all, float(ob['e_per_site'][0]))
             assert all(e == e_all[0] for e in e_all)
+    # ---- odd slice lengths (spin-1, chi = 9: 5 rows of 27 numbers per rank): the ranks' window offsets differ in 16-byte
+    # alignment, the arrival counts must not ----
+    be.shard_mode = 'rows'
+    be.shard_min_rows, be.shard_min_n = 4, 128
+    e_odd = []
+    for shard in (True, False):
+        para = Pm.generate_parameters_dmrg('chain')
+        para.update(spin='one', l=6, chi=9, eigs_tol=1e-12, shard_terms=shard)
+        para = Pm.make_consistent_parameter_dmrg(para)
+        np.random.seed(7)
+        ob, A, info, para = dmrg_finite_size(para)
+        e_odd.append(float(ob['e_per_site'][0]))
+    assert abs(e_odd[0] - e_odd[1]) <= 1e-10 * abs(e_odd[1]), e_odd
     if rank == 0:
-        print('multigpu_check ok: world %d, collectives issued by the library: %d' % (world, comm.collectives()))
+        print('multigpu_check ok: world %d, collectives issued by the library: %d (peer window: %d)' %
+              (world, comm.collectives(), comm.peer_collectives()))
     dist.barrier()
     dist.destroy_process_group()
 

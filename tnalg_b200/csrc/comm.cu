@@ -303,8 +303,9 @@ int comm_allgather_window(tn_comm* c, const double* send, long long count_per_ra
   ++pw->ag_seq;
   const size_t off = base + sizeof(double) * (size_t)count_per_rank * (size_t)c->rank;
   const bool vec2 = (reinterpret_cast<uintptr_t>(send) & 15) == 0 && (off & 15) == 0;
-  const long long work = vec2 ? count_per_rank / 2 : count_per_rank;
-  const int grid = (int)std::max<long long>(1, std::min<long long>((work + 255) / 256, 2LL * sm_count()));
+  // the grid is a function of the slice length alone: every rank counts `grid` arrivals per source, while the 16-byte path
+  // depends on this rank's offset (odd slice lengths put odd ranks on the 8-byte kernel)
+  const int grid = (int)std::max<long long>(1, std::min<long long>((count_per_rank + 511) / 512, 2LL * sm_count()));
   if (vec2) peer_push_kernel<<<grid, 256, 0, stream>>>(pw->view, send, count_per_rank, off);
   else peer_push_kernel_f64<<<grid, 256, 0, stream>>>(pw->view, send, count_per_rank, off);
   TN_LAUNCHED();
