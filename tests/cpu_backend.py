@@ -40,6 +40,14 @@ class GlooComm:
         for t, r in zip(tensors, roots):
             self.dist.broadcast(t, src=r)
 
+    def allgather_inplace(self, buf):
+        per = buf.shape[0] // self.world
+        parts = [torch.empty_like(buf[:per]) for _ in range(self.world)]
+        self.dist.all_gather(parts, buf[self.rank * per:(self.rank + 1) * per].clone())
+        for r, part in enumerate(parts):
+            buf[r * per:(r + 1) * per] = part
+        return buf
+
 
 def shard_groups(g, rank, world):
     """round-robin ownership of the links in the order HL, LS.., HR, RS.., X.. (tn_effh_plan_create); the on-site part
@@ -164,7 +172,7 @@ class CpuBackend:
             return GlooComm(dist)
         return None
 
-    def env_update(self, direction, T, outputs):
+    def env_update(self, direction, T, outputs, outs=None):
         self.n_env_updates += 1
         Tn = T.numpy()
         res = []
@@ -175,6 +183,10 @@ class CpuBackend:
                 v = fn(Tn, None if op is None else np.asarray(op), None if E is None else E.numpy())
                 acc = v if acc is None else acc + v
             res.append(torch.from_numpy(np.ascontiguousarray(acc)))
+        if outs is not None:
+            for o, r in zip(outs, res):
+                o.copy_(r)
+            return outs
         return res
 
     def lincomb(self, xs, coeffs):

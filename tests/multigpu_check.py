@@ -88,6 +88,8 @@ def main():
     for pl in (full, pr, pt):
         pl.destroy()
     # ---- whole sharded runs against the reference goldens, both decompositions ----
+    from tnalg_b200 import envs
+    envs.EnvCache.shard_min_dim = 8                    # sharded bond moves (in-place all-gather of the new blocks) too
     for mode in ('rows', 'terms'):
         be.shard_mode = mode
         be.shard_min_rows, be.shard_min_n = 4, 256     # slice even the small sites of the golden cases

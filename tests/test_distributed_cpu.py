@@ -21,6 +21,8 @@ def _worker(rank, world, port, case, q):
         from tests.test_host_logic_cpu import para_from_golden
         from tnalg_b200 import ops
         from tnalg_b200.DMRG_anyH import dmrg_finite_size
+        from tnalg_b200 import envs
+        envs.EnvCache.shard_min_dim = 4      # exercise the sharded bond moves (in-place all-gather) at chi = 16
         cpu_backend_install(CpuBackend())
         g = dict(np.load(os.path.join(ROOT, 'tests', 'golden', case + '.npz')))
         para = para_from_golden(g)

@@ -106,6 +106,7 @@ class TermTable:
 
 class EnvCache:
     """Left/right blocks of every bond for one TermTable, kept on the device."""
+    shard_min_dim = 64   # bond moves of smaller blocks are computed by every rank (a collective costs more than the GEMMs)
 
     def __init__(self, be, terms, length):
         self.be, self.terms, self.L = be, terms, length
@@ -146,27 +147,24 @@ class EnvCache:
 
     # ---- bond moves ----
     def _env_update(self, direction, T, outputs):
-        """tn_env_update for every outgoing operator of a bond; with several ranks each rank computes the operators
-        j = rank (mod world) and all of them are exchanged in ONE grouped broadcast, so all ranks end up with bit-identical
-        blocks (one writer per operator)"""
+        """tn_env_update for every outgoing operator of a bond; with several ranks the operators are dealt round-robin
+        (heaviest first), every rank writes its own into its rows of one (world * k, e, e) buffer and ONE in-place
+        all-gather completes it on all ranks (one writer per operator: bit-identical blocks everywhere; the blocks
+        handed back are views of that buffer)"""
         comm = self.comm
         e_dim = T.shape[2] if direction == 0 else T.shape[0]
-        if comm is None or comm.world == 1 or len(outputs) < 2 or e_dim < 64:
+        if comm is None or comm.world == 1 or len(outputs) < 2 or e_dim < self.shard_min_dim:
             return self.be.env_update(direction, T, outputs)
         rank, world = comm.rank, comm.world
-        # heaviest outputs first (the H block carries several links), dealt round-robin
         order = sorted(range(len(outputs)), key=lambda j: -len(outputs[j]))
-        owner = {j: i % world for i, j in enumerate(order)}
-        mine = [j for j in range(len(outputs)) if owner[j] == rank]
-        res = [None] * len(outputs)
+        per = (len(outputs) + world - 1) // world
+        buf = self.be.empty(world * per, e_dim, e_dim)
+        place = {j: (i % world) * per + i // world for i, j in enumerate(order)}
+        mine = [j for i, j in enumerate(order) if i % world == rank]
         if mine:
-            for j, mat in zip(mine, self.be.env_update(direction, T, [outputs[j] for j in mine])):
-                res[j] = mat
-        for j in range(len(outputs)):
-            if res[j] is None:
-                res[j] = self.be.empty(e_dim, e_dim)
-        comm.broadcast_many(res, [owner[j] for j in range(len(outputs))])
-        return res
+            self.be.env_update(direction, T, [outputs[j] for j in mine], outs=[buf[place[j]] for j in mine])
+        comm.allgather_inplace(buf)
+        return [buf[place[j]] for j in range(len(outputs))]
 
     def _mirrored(self, live):
         """{(site, s'): (site, s)} for the live operators whose block is the transpose of another live block"""

@@ -119,6 +119,14 @@ class Comm:
                                                     (C.c_longlong * n)(*[t.numel() for t in tensors]),
                                                     (C.c_int * n)(*[int(r) for r in roots]), n, self._be.stream()))
 
+    def allgather_inplace(self, buf):
+        """buf: (world * k, ...) contiguous; rank r has written rows [r*k, (r+1)*k); ONE all-gather fills in the others"""
+        per = buf.numel() // self.world
+        assert buf.is_contiguous() and per * self.world == buf.numel()
+        send = buf.data_ptr() + 8 * per * self.rank
+        L.check(self._be.lib.tn_comm_allgather(self._handle, C.c_void_p(send), _ptr(buf), per, self._be.stream()))
+        return buf
+
     def collectives(self):
         return int(self._be.lib.tn_comm_collectives(self._handle))
 
@@ -223,14 +231,17 @@ class CudaBackend:
         return int(self.lib.tn_launch_count())
 
     # ---- a5: batched environment update ----
-    def env_update(self, direction, T, outputs):
+    def env_update(self, direction, T, outputs, outs=None):
         """outputs: list over outgoing operators of lists of links (E or None, op (d,d) array or None).
-        direction 0: left to right, 1: right to left.  Returns the list of new environment matrices."""
+        direction 0: left to right, 1: right to left.  Returns the list of new environment matrices (written into `outs`
+        -- contiguous (e, e) tensors -- when given)."""
         a, d, b = T.shape
         T = T.contiguous()
         n_out = len(outputs)
         e_dim = b if direction == 0 else a
-        outs = [self.empty(e_dim, e_dim) for _ in range(n_out)]
+        if outs is None:
+            outs = [self.empty(e_dim, e_dim) for _ in range(n_out)]
+        assert len(outs) == n_out and all(o.is_contiguous() and o.shape == (e_dim, e_dim) for o in outs)
         begins, link_E, ops, has_op, keep = [0], [], [], [], []
         for links in outputs:
             for E, op in links:
