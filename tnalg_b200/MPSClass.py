@@ -524,7 +524,7 @@ class MpsOpenBoundaryClass(MpsBasic):
                                      'measure it -- see DESIGN.md, out of scope' % int(sn))
         out = []
         for i in range(0, len(terms), 1024):
-            out.append(expect_products(self._be, self.mps, self.center, ops, terms[i:i + 1024]))
+            out.append(expect_products(self._be, self.mps, self.center, ops, terms[i:i + 1024], comm=self._comm()))
         return np.concatenate(out) if out else np.zeros(0)
 
     def observation_s1(self, inputs):

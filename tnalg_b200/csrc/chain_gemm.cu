@@ -498,7 +498,9 @@ int gemm_plan_schedule(const GemmLaunch& L, ProblemDev* problems, const LinkDev*
   S->ipl = ipl;
   const int tiles = S->tiles_m * S->tiles_n;
   const int ctas_per_sm = large ? TN_CFGL_CTAS : 2;
-  const int max_grid = sms * ctas_per_sm;
+  // launches that share the SMs with a concurrent one (grid_div) take their share of the CTA slots in the small-tile
+  // configuration only: measured -8 % per Lanczos step at chi = 256, +3 % at chi = 512 (large tiles), profiles/r02_small_chi.md
+  const int max_grid = std::max(1, sms * ctas_per_sm / (large ? 1 : std::max(1, L.grid_div)));
 
   long long work = 0, tile_acc = 0, max_tile_iters = 0;
   for (int q = 0; q < L.n_problems; ++q) {

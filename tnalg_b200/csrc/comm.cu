@@ -97,7 +97,11 @@ __device__ __forceinline__ void spin_until_at_least(const unsigned long long* p,
 // buf[i] <- sum over ranks of buf[i], i < count <= kPeerArMax: every rank stores its contribution into slot [ring][rank] of
 // EVERY window, raises the matching flag there, waits for the world's flags in its own window and adds the slots in rank
 // order -- the same order on every rank, so the result is bit-identical everywhere.  One CTA, no NCCL launch.
-__global__ void peer_allreduce_kernel(PeerView pv, double* __restrict__ buf, int count, unsigned long long seq) {
+// pred != nullptr && *pred == 0: the call is skipped -- on EVERY rank, because the flag must derive from all-reduced values
+// (sequence numbers only grow, so a skipped slot is simply never waited for).
+__global__ void peer_allreduce_kernel(PeerView pv, double* __restrict__ buf, int count, unsigned long long seq,
+                                      const int* __restrict__ pred) {
+  if (pred && *pred == 0) return;
   const int tid = threadIdx.x;
   const int ring = (int)(seq % kPeerRing);
   if (tid < count) {
@@ -258,19 +262,22 @@ PeerWindow* peer_window_ensure(tn_comm* c, size_t need, cudaStream_t stream) {
 }
 }  // namespace
 
-int comm_allreduce_sum(tn_comm* c, double* buf, long long count, cudaStream_t stream) {
+bool comm_peer_available(tn_comm* c, cudaStream_t stream) { return c && peer_window_ensure(c, kPeerHeaderBytes, stream) != nullptr; }
+
+int comm_allreduce_sum(tn_comm* c, double* buf, long long count, cudaStream_t stream, const int* pred) {
   TN_REQUIRE(c, "tn_comm: no communicator");
   if (count <= kPeerArMax) {
     PeerWindow* pw = peer_window_ensure(c, kPeerHeaderBytes, stream);
     if (pw) {
       ++pw->ar_seq;
-      peer_allreduce_kernel<<<1, kPeerArMax, 0, stream>>>(pw->view, buf, (int)count, pw->ar_seq);
+      peer_allreduce_kernel<<<1, kPeerArMax, 0, stream>>>(pw->view, buf, (int)count, pw->ar_seq, pred);
       TN_LAUNCHED();
       ++c->n_collectives;
       ++c->n_peer_collectives;
       return TN_OK;
     }
   }
+  TN_REQUIRE(!pred, "tn_comm: a predicated all-reduce needs the peer window");
   TN_CHECK(nccl_allreduce(c, buf, count, stream));
   ++c->n_collectives;
   return TN_OK;

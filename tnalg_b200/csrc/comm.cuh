@@ -6,7 +6,8 @@
 
 namespace tn {
 constexpr int kPeerMaxWorld = 8;          // GPUs of one NVSwitch box
-constexpr int kPeerRing = 4;              // all-reduce slots in flight (every all-reduce is a barrier: 2 would do)
+constexpr int kPeerRing = 4;              // all-reduce slots in flight: an executed all-reduce is a barrier, and callers never skip
+                                          // (predicate) more than one in a row, so a slot is rewritten only after a later barrier
 constexpr int kPeerArMax = 64;            // doubles per small all-reduce
 constexpr size_t kPeerHeaderBytes = 65536;  // flags + all-reduce slots in front of the data region
 
@@ -38,7 +39,11 @@ struct tn_comm {
 };
 
 namespace tn {
-int comm_allreduce_sum(tn_comm* c, double* buf, long long count, cudaStream_t stream);
+// pred (device flag, identical on every rank because it derives from all-reduced values): 0 skips the call everywhere; only
+// with the peer window (comm_peer_available) and count <= kPeerArMax
+int comm_allreduce_sum(tn_comm* c, double* buf, long long count, cudaStream_t stream, const int* pred = nullptr);
+// collective (may set the window up): true when small all-reduces run as peer-window kernels
+bool comm_peer_available(tn_comm* c, cudaStream_t stream);
 // equal contributions: recv holds world * count_per_rank doubles, rank r's block at r * count_per_rank
 int comm_allgather(tn_comm* c, const double* send, double* recv, long long count_per_rank, cudaStream_t stream);
 // same result as comm_allgather, but the gathered vector lives in the library's peer window when that is available (*out points

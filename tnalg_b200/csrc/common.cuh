@@ -140,6 +140,7 @@ struct GemmLaunch {
   int mode, M, N, K, d, lda, ldb, ldc;
   int n_problems, n_links;
   int deterministic;
+  int grid_div;  // > 1: this launch shares the SMs with grid_div - 1 concurrent launches and is scheduled on 1/grid_div of the CTA slots
 };
 // fills work_begin/tile_begin of `problems` (host copies), chooses tile config + split policy.
 struct GemmSchedule {

@@ -200,12 +200,16 @@ static int plan_create_impl(tn_effh_plan** out_plan, int a, int d, int b, const 
   P->overlapAB = P->haveA && P->haveB && n_phi == 0 && P->n_out <= (1LL << 19) && !deterministic_mode() && !getenv("TNALG_NO_OVERLAP");
   if (P->overlapAB)
     for (auto& q : pa) q.shared_out = 1;
+  // concurrent stages in the small-tile configuration: each is cut for half of the CTA slots, which halves the number of
+  // partial tiles combined with FP64 atomics and of pipeline fills compared with two full-size grids queuing behind each other
+  static const int overlap_div = getenv("TNALG_OVERLAP_GRID_DIV") ? atoi(getenv("TNALG_OVERLAP_GRID_DIV")) : 2;
+  const int grid_div = P->overlapAB ? std::max(1, overlap_div) : 1;
   const double* fake_psi = reinterpret_cast<const double*>(uintptr_t(256));  // alignment stand-in for scheduling
   const double* fake_slice = fake_psi + (P->off & 1);                         // the right stage reads psi + off
   const bool use_tma = tma_available() && !getenv("TNALG_NO_TMA");
   std::vector<TmaMap> hmaps;
   if (P->haveA) {
-    P->LA = GemmLaunch{TN_NN, a_out, d * b, a, dl, a, d * b, d * b, (int)pa.size(), (int)la.size(), deterministic_mode() ? 1 : 0};
+    P->LA = GemmLaunch{TN_NN, a_out, d * b, a, dl, a, d * b, d * b, (int)pa.size(), (int)la.size(), deterministic_mode() ? 1 : 0, grid_div};
     int st = gemm_plan_schedule(P->LA, pa.data(), la.data(), fake_psi, fake_psi, &P->SA);
     if (st != TN_OK) { delete P; return st; }
     if (use_tma && P->SA.config == 0 && P->SA.aligned16) {  // left stage: A = environment matrix (a x a), B = psi (per call)
@@ -254,7 +258,7 @@ static int plan_create_impl(tn_effh_plan** out_plan, int a, int d, int b, const 
       q.shared_out = (nl > kChunk || P->overlapAB) ? 1 : 0;
       pb.push_back(q);
     }
-    P->LB = GemmLaunch{TN_NT, a_out * d, b, b, dl, b, b, b, (int)pb.size(), nl, deterministic_mode() ? 1 : 0};
+    P->LB = GemmLaunch{TN_NT, a_out * d, b, b, dl, b, b, b, (int)pb.size(), nl, deterministic_mode() ? 1 : 0, grid_div};
     int st = gemm_plan_schedule(P->LB, pb.data(), lb.data(), fake_slice, fake_psi, &P->SB);
     if (st != TN_OK) { delete P; return st; }
     if (use_tma && P->SB.config == 0 && P->SB.aligned16) {  // right stage: A = psi (per call) or Phi_i, B = environment matrix (b x b)

@@ -61,8 +61,10 @@ __global__ void lanczos_dgks_kernel(LanczosState* st, int j) {
   for (int i = 0; i <= j; ++i) s += st->h[i] * st->h[i];
   const int need = !((ww - s) > 0.5 * ww);
   st->need2 = need;
-  if (!need)
+  if (!need) {
     for (int i = 0; i <= j; ++i) st->h2[i] = 0.0;
+    st->h2[j + 1] = ww - s;   // |w'|^2 by Pythagoras (read by the sliced path in place of the measured w'.w')
+  }
 }
 
 // after the two CGS passes and the norm of step j
@@ -466,6 +468,8 @@ static int lanczos_core(LanczosOp& op, long long n, long long n_loc, long long o
       if (per_sm * sms < fused_grid) fused_grid = 0;  // cannot be co-resident: use the streaming path
     }
   }
+  // sliced basis: with the peer window the second Gram-Schmidt pass is predicated on the device (DGKS)
+  const bool peer_pred = sliced && m + 2 <= kPeerArMax && !getenv("TNALG_NO_DGKS_SKIP") && comm_peer_available(comm, stream);
   int n_matvec = 0;
   int j0 = 0;
   LanczosStatus hs{};
@@ -476,7 +480,22 @@ static int lanczos_core(LanczosOp& op, long long n, long long n_loc, long long o
       TN_CHECK(op.apply(vec(j), w, stream));
       ++n_matvec;
       TN_CHECK(project_locked(w));
-      if (sliced) {
+      if (sliced && peer_pred) {
+        // sliced basis, collectives in the peer window: the DGKS flag derives from all-reduced numbers (identical on every
+        // rank), so the second Gram-Schmidt pass AND its all-reduce are skipped on the device when the first pass removed
+        // less than half of |w|^2; |w'|^2 = |w|^2 - sum h^2 then stands in for the measured norm (h2[j+1])
+        TN_CHECK(launch_multidot(V, ldv, j + 2, w, n_loc, st->h, partial, counter, stream));
+        TN_CHECK(reduce(st->h, j + 2));
+        lanczos_dgks_kernel<<<1, 1, 0, stream>>>(st, j);
+        TN_LAUNCHED();
+        TN_CHECK(launch_multi_axpy(w, V, ldv, j + 1, st->h, n_loc, stream));
+        TN_CHECK(launch_multidot(V, ldv, j + 2, w, n_loc, st->h2, partial, counter, stream, &st->need2));
+        TN_CHECK(comm_allreduce_sum(comm, st->h2, j + 2, stream, &st->need2));
+        TN_CHECK(launch_multi_axpy(w, V, ldv, j + 1, st->h2, n_loc, stream, &st->need2));
+        lanczos_finish_sharded_kernel<<<1, 1, 0, stream>>>(st, j);
+        TN_LAUNCHED();
+        TN_CHECK(launch_scale_dev(w, &st->inv_beta, n_loc, stream));
+      } else if (sliced) {
         // sliced basis: full CGS2 with two small all-reduces per step (h and w.w; h2 and w'.w')
         TN_CHECK(launch_multidot(V, ldv, j + 2, w, n_loc, st->h, partial, counter, stream));
         TN_CHECK(reduce(st->h, j + 2));

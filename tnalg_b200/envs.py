@@ -385,7 +385,30 @@ class EnvCache:
         return plan
 
 
-def expect_products(be, mps, center, ops, terms):
+def expect_products(be, mps, center, ops, terms, comm=None, min_terms=16):
+    """expectation values of operator products (see _expect_products_local).  With a communicator (bit-identical replicas on
+    several GPUs) the terms are dealt to the ranks by their leading site, every rank contracts its share, and one all-reduce of the value vector (each entry has exactly one
+    non-zero contribution, so the sum is exact and identical everywhere) completes the result on all ranks."""
+    if comm is None or comm.world == 1 or len(terms) < min_terms:
+        return _expect_products_local(be, mps, center, ops, terms)
+    # contiguous blocks of leading sites, balanced by the number of bonds the terms' environments live on: terms that share
+    # a prefix environment (same leading site) stay together and the closing blocks a rank needs cluster around its sites
+    L = len(mps)
+    weight = np.zeros(L)
+    for term in terms:
+        weight[int(term[0][0])] += 1 + int(term[-1][0]) - int(term[0][0])
+    cum = np.cumsum(weight)
+    owner = [min(comm.world - 1, int((cum[s] - weight[s] / 2) * comm.world / cum[-1])) for s in range(L)]
+    mine = [i for i, term in enumerate(terms) if owner[int(term[0][0])] == comm.rank]
+    vals = np.zeros(len(terms))
+    if mine:
+        vals[mine] = _expect_products_local(be, mps, center, ops, [terms[i] for i in mine])
+    buf = be.from_numpy(vals)
+    comm.allreduce(buf)
+    return be.to_numpy(buf)
+
+
+def _expect_products_local(be, mps, center, ops, terms):
     """<prod_k op[s_k](site_k)> for every term in `terms` (list of tuples of (site, op_id), sites strictly increasing
     inside a term) on a centre-orthogonal MPS (sites < center left-, sites > center right-orthonormal).
     a10: observation_s1 / observation_s1_s2 (MPSClass.py:857-909) restated as one left-to-right pass:
