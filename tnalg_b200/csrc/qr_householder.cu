@@ -34,6 +34,7 @@ namespace tn {
 namespace {
 constexpr int QNB = 32;        // panel width
 constexpr int QMAXC = 8;       // portable cluster size
+constexpr int QMAXC_PANEL = 16; // panel kernel: non-portable cluster size (used only when the device can co-schedule it)
 constexpr int QSLOT = 2 * QNB; // doubles one CTA contributes per column: g[32], row j[32]
 constexpr int QMAX_RPT = 48;   // rows per thread of the panel kernel -> 768 rows per CTA, 6144 per cluster
 constexpr int QNC = 32;        // strip width of the apply kernel
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) qr_panel_kernel(double* __restr
   const int C = (int)cluster.num_blocks(), c = (int)cluster.block_rank();
   __shared__ double red[2][WARPS][QNB];        // per-warp partial Gram rows
   __shared__ double rowj[2][QNB];               // row j of the panel (CTA 0)
-  __shared__ double slots[2][QMAXC][QSLOT];     // cluster exchange: [parity][source CTA][g(32) | row j(32)]
+  __shared__ double slots[2][QMAXC_PANEL][QSLOT];     // cluster exchange: [parity][source CTA][g(32) | row j(32)]
   __shared__ double Z[QNB * QNB];               // Z[k*32 + j] = V_k^T v_j (k < j)
   __shared__ double Ts[QNB * QNB];              // compact-WY factor
   __shared__ double taus[QNB];
@@ -615,19 +616,49 @@ static int launch_panel_t(double* W, int ld, int m, int j0, int nbp, double* tau
   return TN_OK;
 }
 
+// largest cluster the panel kernel may use: 16 CTAs (non-portable size) when the device can co-schedule such a cluster, else 8
+static int panel_max_cluster() {
+  static int v = 0;
+  if (v) return v;
+  v = QMAXC;
+  if (!getenv("TNALG_QR_CLUSTER16")) return v;   // measured: no gain over 8 x 256 rows at 2048 x 1024 (3.32 vs 3.34 ms), kept opt-in
+  auto kern = qr_panel_kernel<16, true, 8>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return v; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(QMAXC_PANEL);
+  cfg.blockDim = dim3(8 * 32);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = QMAXC_PANEL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n_clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return v; }
+  if (n_clusters >= 1) v = QMAXC_PANEL;
+  return v;
+}
+
 static int launch_panel(double* W, int ld, int m, int j0, int nbp, double* tau, double* T, cudaStream_t stream) {
   const int rows = m - j0;
   // Up to 2048 rows: 8 warps per CTA, 256 rows per CTA (32 per thread, the column-j broadcasts of phase A kept for the update),
   // a cluster of 1 / 2 / 4 / 8 CTAs.  The per-column cost is instruction issue: few warps keep the redundant scalar work small.
   // Taller panels: 16 warps, up to 768 rows per CTA (6144 per cluster).
+  // rows per CTA: the per-column cost is instruction issue inside the CTA (shuffles + FMAs over the thread's rows) plus one
+  // cluster exchange whose latency does not depend on the cluster size, so small slices win: 128 rows per CTA measured
+  // 10 % faster than 256 (profiles/r02_qr.md); a 16-CTA cluster (128-row slices of 2048 rows) only with 16-row threads
+  static const int cta_rows = getenv("TNALG_QR_PANEL_CTA_ROWS") ? std::max(32, atoi(getenv("TNALG_QR_PANEL_CTA_ROWS"))) : 128;
+  const int max_c = panel_max_cluster();
   int C = 1;
-  while (C < QMAXC && (rows + C - 1) / C > 256 && rows / (2 * C) >= QNB) C *= 2;
+  while (C < max_c && (rows + C - 1) / C > cta_rows && rows / (2 * C) >= QNB) C *= 2;
+  if (C > QMAXC && (rows + C - 1) / C > 128) C = QMAXC;   // the 16-CTA attribute is set on the <16, true, 8> instantiation only
   const int per_cta = (rows + C - 1) / C;
   TN_REQUIRE(C == 1 || per_cta >= QNB, "tn_qr: internal panel split");
   if (per_cta <= 256) {
     const int rpt = (per_cta + 7) / 8;
-    if (rpt <= 4) return launch_panel_t<4, true, 8>(W, ld, m, j0, nbp, tau, T, C, stream);
-    if (rpt <= 8) return launch_panel_t<8, true, 8>(W, ld, m, j0, nbp, tau, T, C, stream);
+    if (rpt <= 4 && C <= QMAXC) return launch_panel_t<4, true, 8>(W, ld, m, j0, nbp, tau, T, C, stream);
+    if (rpt <= 8 && C <= QMAXC) return launch_panel_t<8, true, 8>(W, ld, m, j0, nbp, tau, T, C, stream);
     if (rpt <= 16) return launch_panel_t<16, true, 8>(W, ld, m, j0, nbp, tau, T, C, stream);
     return launch_panel_t<32, true, 8>(W, ld, m, j0, nbp, tau, T, C, stream);
   }
@@ -642,8 +673,9 @@ static int launch_apply(const double* Wv, int ldv, int m, int j0, int nbp, const
   if (c_end <= c_begin || m - j0 <= 0) return TN_OK;
   const int rows = m - j0;
   const int strips = (c_end - c_begin + QNC - 1) / QNC;
+  static const int apply_rows = getenv("TNALG_QR_APPLY_CTA_ROWS") ? std::max(32, atoi(getenv("TNALG_QR_APPLY_CTA_ROWS"))) : 128;   // 128-row slices: one staging pass per CTA (-5 % at 512 x 256)
   int CR = 1;
-  while (CR < QMAXC && (rows + CR - 1) / CR > 256) CR *= 2;
+  while (CR < QMAXC && (rows + CR - 1) / CR > apply_rows) CR *= 2;
   const int RB = ((rows + CR - 1) / CR + 7) / 8 * 8;
   const size_t fixed = sizeof(double) * ((size_t)QNB * QNB + (size_t)CR * QNB * QNC + 2 * (size_t)QNB * QNC);
   const size_t cap = 227 * 1024;
