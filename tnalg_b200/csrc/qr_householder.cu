@@ -34,7 +34,6 @@ namespace tn {
 namespace {
 constexpr int QNB = 32;        // panel width
 constexpr int QMAXC = 8;       // portable cluster size
-constexpr int QMAXC_PANEL = 16; // panel kernel: non-portable cluster size (used only when the device can co-schedule it)
 constexpr int QSLOT = 2 * QNB; // doubles one CTA contributes per column: g[32], row j[32]
 constexpr int QMAX_RPT = 48;   // rows per thread of the panel kernel -> 768 rows per CTA, 6144 per cluster
 constexpr int QNC = 32;        // strip width of the apply kernel
@@ -100,7 +99,8 @@ __device__ long long g_qr_aclk[8];   // apply kernel: phases 0..6, [7] = launche
 
 template <int RPT, bool KEEP, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) qr_panel_kernel(double* __restrict__ W, int ld, int m, int j0, int nbp,
-                                                               double* __restrict__ tau_out, double* __restrict__ T_out) {
+                                                               double* __restrict__ tau_out, double* __restrict__ T_out,
+                                                               const double* __restrict__ Tprev) {
 #ifdef TN_QR_TIMING
   long long tclk_ = clock64();
 #endif
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) qr_panel_kernel(double* __restr
   const int C = (int)cluster.num_blocks(), c = (int)cluster.block_rank();
   __shared__ double red[2][WARPS][QNB];        // per-warp partial Gram rows
   __shared__ double rowj[2][QNB];               // row j of the panel (CTA 0)
-  __shared__ double slots[2][QMAXC_PANEL][QSLOT];     // cluster exchange: [parity][source CTA][g(32) | row j(32)]
+  __shared__ double slots[2][QMAXC][QSLOT];     // cluster exchange: [parity][source CTA][g(32) | row j(32)]
   __shared__ double Z[QNB * QNB];               // Z[k*32 + j] = V_k^T v_j (k < j)
   __shared__ double Ts[QNB * QNB];              // compact-WY factor
   __shared__ double taus[QNB];
@@ -136,6 +136,140 @@ __global__ void __launch_bounds__(WARPS * 32, 1) qr_panel_kernel(double* __restr
   }
   __syncthreads();
   if (C > 1) cluster_barrier();  // every CTA of the cluster is resident (and its mbarriers live) before remote stores start
+
+  // ---- fused look-ahead: the block reflector of the PREVIOUS panel (columns [j0-32, j0), rows [j0-32, m), factor Tprev) is
+  // applied to this panel's columns while they sit in the registers,  X <- X - V (Tprev^T (V^T X)),  instead of by a separate
+  // launch on the critical path between two panels (~20 us of launch + latency chain per panel).  The 32 rows above the panel
+  // (they become rows of R) are carried by CTA 0 as four extra row slots per thread.
+  extern __shared__ __align__(16) double fz[];
+  if constexpr (KEEP) if (Tprev != nullptr) {
+    constexpr int ROWS = RPT * WARPS;                  // rows of this CTA
+    double* Vs = fz;                                   // [ROWS][32]   previous reflectors, rows of this CTA (all below their diagonal block)
+    double* Vt = Vs + ROWS * QNB;                      // [32][32]     unit-lower-triangular diagonal block (CTA 0)
+    double* Tp = Vt + QNB * QNB;                       // [32][32]
+    double* Wtot = Tp + QNB * QNB;                     // [32][32]     V^T X summed over the cluster
+    double* Yn = Wtot + QNB * QNB;                     // [32][32]     -Tprev^T Wtot
+    double* part = Yn + QNB * QNB;                     // [WARPS][8][32] per-warp partial rows of V^T X (one round of 8 reflectors)
+    double* Wex = part + WARPS * 8 * QNB;              // [C][32][32]  cluster exchange
+    const int jp = j0 - QNB;                           // first column / row of the previous panel
+    double xt[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      xt[t] = (c == 0 && lane < nbp) ? W[(size_t)(jp + t * WARPS + warp) * ld + j0 + lane] : 0.0;
+    {
+      double v[RPT];
+#pragma unroll
+      for (int u = 0; u < RPT; ++u) {                  // element idx = r*32 + q, one deep batch of independent loads
+        const int idx = u * (WARPS * 32) + tid, r = idx >> 5, q = idx & 31;
+        v[u] = (row_lo + r < rows_total) ? W[(size_t)(j0 + row_lo + r) * ld + jp + q] : 0.0;
+      }
+      double vt4[4], tp4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = u * (WARPS * 32) + tid, r = idx >> 5, q = idx & 31;
+        vt4[u] = (c == 0 && r > q) ? W[(size_t)(jp + r) * ld + jp + q] : (r == q ? 1.0 : 0.0);
+        tp4[u] = Tprev[idx];
+      }
+#pragma unroll
+      for (int u = 0; u < RPT; ++u) Vs[u * (WARPS * 32) + tid] = v[u];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        Vt[u * (WARPS * 32) + tid] = vt4[u];
+        Tp[u * (WARPS * 32) + tid] = tp4[u];
+      }
+    }
+    __syncthreads();
+    // V^T X over this thread's rows: acc[q] = sum_i V[row_i, q] x[i]  (column `lane` of X); the V row is a shared-memory broadcast
+    double acc[QNB];
+#pragma unroll
+    for (int q = 0; q < QNB; ++q) acc[q] = 0.0;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const double2* vr = reinterpret_cast<const double2*>(Vs + (i * WARPS + warp) * QNB);
+#pragma unroll
+      for (int q2 = 0; q2 < QNB / 2; ++q2) {
+        const double2 vv = vr[q2];
+        acc[2 * q2] = fma(vv.x, x[i], acc[2 * q2]);
+        acc[2 * q2 + 1] = fma(vv.y, x[i], acc[2 * q2 + 1]);
+      }
+    }
+    if (c == 0) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const double2* vr = reinterpret_cast<const double2*>(Vt + (t * WARPS + warp) * QNB);
+#pragma unroll
+        for (int q2 = 0; q2 < QNB / 2; ++q2) {
+          const double2 vv = vr[q2];
+          acc[2 * q2] = fma(vv.x, xt[t], acc[2 * q2]);
+          acc[2 * q2 + 1] = fma(vv.y, xt[t], acc[2 * q2 + 1]);
+        }
+      }
+    }
+    // sum over the warps (fixed order), 8 reflectors per round, and hand this CTA's partial to slot c of every CTA
+#pragma unroll
+    for (int rd = 0; rd < QNB / 8; ++rd) {
+#pragma unroll
+      for (int qq = 0; qq < 8; ++qq) part[(warp * 8 + qq) * QNB + lane] = acc[rd * 8 + qq];
+      __syncthreads();
+      {
+        double sacc = 0.0;
+#pragma unroll
+        for (int w2 = 0; w2 < WARPS; ++w2) sacc += part[w2 * 8 * QNB + tid];   // tid = qq*32 + k
+        const int e = rd * 8 * QNB + tid;
+        if (C == 1) {
+          Wex[e] = sacc;
+        } else {
+          for (int dst = 0; dst < C; ++dst) cluster.map_shared_rank(Wex, dst)[c * QNB * QNB + e] = sacc;
+        }
+      }
+      __syncthreads();
+    }
+    if (C > 1) cluster_barrier();
+    for (int e = tid; e < QNB * QNB; e += WARPS * 32) {
+      double sacc = 0.0;
+      for (int src = 0; src < C; ++src) sacc += Wex[src * QNB * QNB + e];
+      Wtot[e] = sacc;
+    }
+    __syncthreads();
+    for (int e = tid; e < QNB * QNB; e += WARPS * 32) {
+      const int i = e >> 5, cc = e & 31;
+      double s4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int k = 0; k < QNB; ++k) s4[k & 3] = fma(Tp[k * QNB + i], Wtot[k * QNB + cc], s4[k & 3]);
+      Yn[e] = -((s4[0] + s4[1]) + (s4[2] + s4[3]));
+    }
+    __syncthreads();
+    // X += V Yn
+#pragma unroll
+    for (int q = 0; q < QNB; ++q) acc[q] = Yn[q * QNB + lane];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const double2* vr = reinterpret_cast<const double2*>(Vs + (i * WARPS + warp) * QNB);
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int q2 = 0; q2 < QNB / 2; ++q2) {
+        const double2 vv = vr[q2];
+        s0 = fma(vv.x, acc[2 * q2], s0);
+        s1 = fma(vv.y, acc[2 * q2 + 1], s1);
+      }
+      x[i] += s0 + s1;
+    }
+    if (c == 0) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const double2* vr = reinterpret_cast<const double2*>(Vt + (t * WARPS + warp) * QNB);
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int q2 = 0; q2 < QNB / 2; ++q2) {
+          const double2 vv = vr[q2];
+          s0 = fma(vv.x, acc[2 * q2], s0);
+          s1 = fma(vv.y, acc[2 * q2 + 1], s1);
+        }
+        if (lane < nbp) W[(size_t)(jp + t * WARPS + warp) * ld + j0 + lane] = xt[t] + (s0 + s1);
+      }
+    }
+    // columns >= nbp of a narrow last panel carried zeros and stay zero (x = 0 there, Yn column 0)
+  }
   QR_CLK(0);
 
   double myscale = 0.0;  // 1 / (alpha - beta) of column `lane`: the reflector tails stay unscaled in the registers until the write-back
@@ -584,6 +718,7 @@ __global__ void qr_build_s_kernel(const double* __restrict__ Gp, int n_split, si
 struct QrSide {
   cudaStream_t s = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t join2[2] = {nullptr, nullptr};   // fused look-ahead: wide updates of even / odd panels
 };
 static QrSide* qr_side() {
   static QrSide x;
@@ -591,18 +726,37 @@ static QrSide* qr_side() {
     if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&x.join2[0], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&x.join2[1], cudaEventDisableTiming) != cudaSuccess) return nullptr;
   }
   return &x;
 }
 
 static int grid_for(long long n) { return (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8); }
 
+// dynamic shared memory of the fused look-ahead (qr_panel_kernel with Tprev): reflector rows, diagonal block, T, V^T X, its
+// image under -T^T, one reduction round and the cluster exchange
+static size_t panel_fused_smem(int rpt, int C) {
+  return sizeof(double) * ((size_t)rpt * 8 * QNB + 4 * (size_t)QNB * QNB + 8 * 8 * QNB + (size_t)C * QNB * QNB);
+}
+
 template <int RPT, bool KEEP, int WARPS>
-static int launch_panel_t(double* W, int ld, int m, int j0, int nbp, double* tau, double* T, int C, cudaStream_t stream) {
+static int launch_panel_t(double* W, int ld, int m, int j0, int nbp, double* tau, double* T, const double* Tprev, int C,
+                          cudaStream_t stream) {
+  size_t smem = 0;
+  if (Tprev) {
+    TN_REQUIRE(KEEP && WARPS == 8 && j0 >= QNB, "tn_qr: internal: fused look-ahead on an unsupported panel configuration");
+    smem = panel_fused_smem(RPT, C);
+    static size_t configured = 0;
+    if (smem > configured) {
+      TN_CUDA(cudaFuncSetAttribute(qr_panel_kernel<RPT, KEEP, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(190 * 1024)));
+      configured = 190 * 1024;
+    }
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(C);
   cfg.blockDim = dim3(WARPS * 32);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -611,61 +765,43 @@ static int launch_panel_t(double* W, int ld, int m, int j0, int nbp, double* tau
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  TN_CUDA(cudaLaunchKernelEx(&cfg, qr_panel_kernel<RPT, KEEP, WARPS>, W, ld, m, j0, nbp, tau, T));
+  TN_CUDA(cudaLaunchKernelEx(&cfg, qr_panel_kernel<RPT, KEEP, WARPS>, W, ld, m, j0, nbp, tau, T, Tprev));
   TN_LAUNCHED();
   return TN_OK;
 }
 
-// largest cluster the panel kernel may use: 16 CTAs (non-portable size) when the device can co-schedule such a cluster, else 8
-static int panel_max_cluster() {
-  static int v = 0;
-  if (v) return v;
-  v = QMAXC;
-  if (!getenv("TNALG_QR_CLUSTER16")) return v;   // measured: no gain over 8 x 256 rows at 2048 x 1024 (3.32 vs 3.34 ms), kept opt-in
-  auto kern = qr_panel_kernel<16, true, 8>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return v; }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(QMAXC_PANEL);
-  cfg.blockDim = dim3(8 * 32);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = QMAXC_PANEL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  int n_clusters = 0;
-  if (cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return v; }
-  if (n_clusters >= 1) v = QMAXC_PANEL;
-  return v;
-}
-
-static int launch_panel(double* W, int ld, int m, int j0, int nbp, double* tau, double* T, cudaStream_t stream) {
+// Tprev != nullptr: the kernel first applies the previous panel's block reflector to its own columns (8-warp variants only: see
+// panel_can_fuse)
+static int launch_panel(double* W, int ld, int m, int j0, int nbp, double* tau, double* T, const double* Tprev, cudaStream_t stream) {
   const int rows = m - j0;
   // Up to 2048 rows: 8 warps per CTA, 256 rows per CTA (32 per thread, the column-j broadcasts of phase A kept for the update),
   // a cluster of 1 / 2 / 4 / 8 CTAs.  The per-column cost is instruction issue: few warps keep the redundant scalar work small.
   // Taller panels: 16 warps, up to 768 rows per CTA (6144 per cluster).
   // rows per CTA: the per-column cost is instruction issue inside the CTA (shuffles + FMAs over the thread's rows) plus one
   // cluster exchange whose latency does not depend on the cluster size, so small slices win: 128 rows per CTA measured
-  // 10 % faster than 256 (profiles/r02_qr.md); a 16-CTA cluster (128-row slices of 2048 rows) only with 16-row threads
+  // 10 % faster than 256 (profiles/r02_qr.md; a non-portable 16-CTA cluster for 2048 rows measured no further gain)
   static const int cta_rows = getenv("TNALG_QR_PANEL_CTA_ROWS") ? std::max(32, atoi(getenv("TNALG_QR_PANEL_CTA_ROWS"))) : 128;
-  const int max_c = panel_max_cluster();
   int C = 1;
-  while (C < max_c && (rows + C - 1) / C > cta_rows && rows / (2 * C) >= QNB) C *= 2;
-  if (C > QMAXC && (rows + C - 1) / C > 128) C = QMAXC;   // the 16-CTA attribute is set on the <16, true, 8> instantiation only
+  while (C < QMAXC && (rows + C - 1) / C > cta_rows && rows / (2 * C) >= QNB) C *= 2;
   const int per_cta = (rows + C - 1) / C;
   TN_REQUIRE(C == 1 || per_cta >= QNB, "tn_qr: internal panel split");
   if (per_cta <= 256) {
     const int rpt = (per_cta + 7) / 8;
-    if (rpt <= 4 && C <= QMAXC) return launch_panel_t<4, true, 8>(W, ld, m, j0, nbp, tau, T, C, stream);
-    if (rpt <= 8 && C <= QMAXC) return launch_panel_t<8, true, 8>(W, ld, m, j0, nbp, tau, T, C, stream);
-    if (rpt <= 16) return launch_panel_t<16, true, 8>(W, ld, m, j0, nbp, tau, T, C, stream);
-    return launch_panel_t<32, true, 8>(W, ld, m, j0, nbp, tau, T, C, stream);
+    if (rpt <= 4) return launch_panel_t<4, true, 8>(W, ld, m, j0, nbp, tau, T, Tprev, C, stream);
+    if (rpt <= 8) return launch_panel_t<8, true, 8>(W, ld, m, j0, nbp, tau, T, Tprev, C, stream);
+    if (rpt <= 16) return launch_panel_t<16, true, 8>(W, ld, m, j0, nbp, tau, T, Tprev, C, stream);
+    return launch_panel_t<32, true, 8>(W, ld, m, j0, nbp, tau, T, Tprev, C, stream);
   }
   const int rpt = (per_cta + 15) / 16;
   TN_REQUIRE(rpt <= QMAX_RPT, "tn_qr: %d rows exceed the panel capacity (%d rows)", rows, QMAXC * QMAX_RPT * 16);
-  if (rpt <= 32) return launch_panel_t<32, false, 16>(W, ld, m, j0, nbp, tau, T, C, stream);
-  return launch_panel_t<QMAX_RPT, false, 16>(W, ld, m, j0, nbp, tau, T, C, stream);
+  if (rpt <= 32) return launch_panel_t<32, false, 16>(W, ld, m, j0, nbp, tau, T, Tprev, C, stream);
+  return launch_panel_t<QMAX_RPT, false, 16>(W, ld, m, j0, nbp, tau, T, Tprev, C, stream);
+}
+
+// the panel of `rows` rows runs on an 8-warp variant (<= 256 rows per CTA of a cluster of <= 8): the fused look-ahead is available
+static bool panel_can_fuse(int rows) {
+  if (rows < QNB) return false;
+  return (rows + QMAXC - 1) / QMAXC <= 256;
 }
 
 static int launch_apply(const double* Wv, int ldv, int m, int j0, int nbp, const double* T, int transT, double* Cm, int ldc,
@@ -860,10 +996,41 @@ extern "C" int tn_qr_householder(const double* A, int m, int n, int trans_in, do
   // remaining columns then runs on a side stream while panel p+1 (latency bound, a handful of SMs) is factored on the main stream
   const int dbg_skip = qr_debug_skip();   // timing builds only: 1 = no Q formation, 2 = no wide trailing updates, 4 = no look-ahead updates, 8 = no panels
   QrSide* side = (panels > 2 && n > 4 * QNB && !getenv("TNALG_QR_NO_LOOKAHEAD")) ? qr_side() : nullptr;
+  static const bool no_fuse = getenv("TNALG_QR_NO_FUSE") != nullptr;
+  const bool fused = !no_fuse && !dbg_skip && panels >= 2 && panel_can_fuse(m - QNB);
+  if (fused) {
+    // Fused look-ahead: panel p applies the reflectors of panel p-1 to its OWN columns inside the panel kernel; the wide update
+    // with the reflectors of panel p (columns from panel p+2 on; everything to the right for the last panel) runs on the side
+    // stream concurrently with panel p+1.  Panel p needs the wide update p-2 (the last one that touched its columns).
+    bool rec[2] = {false, false};
+    for (int p = 0; p < panels; ++p) {
+      const int j0 = p * QNB, nbp = std::min(QNB, k - j0);
+      double* Tp = Tall + (size_t)p * QNB * QNB;
+      if (side && p >= 2 && rec[p & 1]) TN_CUDA(cudaStreamWaitEvent(stream, side->join2[p & 1], 0));
+      TN_CHECK(launch_panel(W, n, m, j0, nbp, tau, Tp, p > 0 ? Tp - QNB * QNB : nullptr, stream));
+      const int nb_next = std::min(QNB, k - (j0 + nbp));   // the next panel takes exactly its own columns
+      const int c_begin = (p + 1 < panels) ? j0 + nbp + nb_next : j0 + nbp;
+      if (c_begin >= n) continue;
+      if (side) {
+        TN_CUDA(cudaEventRecord(side->fork, stream));
+        TN_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
+        TN_CHECK(launch_apply(W, n, m, j0, nbp, Tp, 1, W, n, c_begin, n, side->s));
+        TN_CUDA(cudaEventRecord(side->join2[p & 1], side->s));
+        rec[p & 1] = true;
+      } else {
+        TN_CHECK(launch_apply(W, n, m, j0, nbp, Tp, 1, W, n, c_begin, n, stream));
+      }
+    }
+    if (side) {   // all wide updates done before R and Q are read (the side stream is in order: the last record covers them all)
+      const int last = rec[(panels - 1) & 1] ? ((panels - 1) & 1) : ((panels - 2) & 1);
+      if (rec[last]) TN_CUDA(cudaStreamWaitEvent(stream, side->join2[last], 0));
+      if (rec[last ^ 1]) TN_CUDA(cudaStreamWaitEvent(stream, side->join2[last ^ 1], 0));
+    }
+  } else
   for (int p = 0; p < panels; ++p) {
     const int j0 = p * QNB, nbp = std::min(QNB, k - j0);
     const double* Tp = Tall + (size_t)p * QNB * QNB;
-    if (!(dbg_skip & 8)) TN_CHECK(launch_panel(W, n, m, j0, nbp, tau, Tall + (size_t)p * QNB * QNB, stream));
+    if (!(dbg_skip & 8)) TN_CHECK(launch_panel(W, n, m, j0, nbp, tau, Tall + (size_t)p * QNB * QNB, nullptr, stream));
     const int next_end = std::min(n, j0 + nbp + QNB);
     if (!side || next_end >= n) {
       if (side && p > 0) TN_CUDA(cudaStreamWaitEvent(stream, side->join, 0));
