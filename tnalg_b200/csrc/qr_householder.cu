@@ -874,22 +874,60 @@ static int qr_fullt_min_panels() {
 }
 static size_t qr_gemm_slot_bytes() { return align_up(tn_chain_gemm_workspace_bytes(32, 32)); }
 
-struct QrGemmCall {
-  std::vector<tn_problem> pr;
-  std::vector<tn_link> ln;
-  void add(const double* A, const double* B, double* Cm, double alpha, int accumulate) {
-    tn_link l = {};
-    l.A = A; l.B = B; l.has_op = 0;
-    tn_problem q = {};
-    q.C = Cm; q.alpha = alpha; q.link_begin = (int)ln.size(); q.link_count = 1; q.accumulate = accumulate;
-    ln.push_back(l);
-    pr.push_back(q);
+// The GEMMs of the Q formation are tiny and strictly ordered: their descriptors (problem / link tables of the chain GEMM) hold
+// only workspace addresses, so ALL of them are built on the host first and reach the device in ONE copy; the launches then
+// follow each other without a host-to-device transfer in between (ten calls of tn_chain_gemm cost two copies each, ~80 us of a
+// 0.6 ms factorisation at 512 x 256).
+struct QrGemmBatch {
+  struct Call {
+    GemmLaunch L;
+    GemmSchedule S;
+  };
+  std::vector<Call> calls;
+  std::vector<char> host;
+  char* dev = nullptr;
+  size_t slot_bytes = 0, link_off = 0;
+  std::vector<ProblemDev> ph;
+  std::vector<LinkDev> lh;
+
+  explicit QrGemmBatch(char* dev_slots) : dev(dev_slots) {
+    slot_bytes = qr_gemm_slot_bytes();
+    link_off = align_up(sizeof(ProblemDev) * 32);
   }
-  int run(int mode, int M, int N, int K, int lda, int ldb, int ldc, void* slot, cudaStream_t stream) {
-    if (pr.empty()) return TN_OK;
-    TN_REQUIRE(pr.size() <= 32, "tn_qr: too many blocks in one batched product");
-    return tn_chain_gemm(mode, M, N, K, 1, lda, ldb, ldc, pr.data(), (int)pr.size(), ln.data(), (int)ln.size(), 1, slot,
-                         qr_gemm_slot_bytes(), stream);
+  void begin() { ph.clear(); lh.clear(); }
+  void add(const double* A, const double* B, double* Cm, double alpha, int accumulate) {
+    LinkDev l = {};
+    l.A = A; l.B = B; l.has_op = 0;
+    ProblemDev q = {};
+    q.C = Cm; q.alpha = alpha; q.link_begin = (int)lh.size(); q.link_count = 1; q.accumulate = accumulate;
+    lh.push_back(l);
+    ph.push_back(q);
+  }
+  // closes the call opened by begin(); returns its index (-1: no block in it), or a negative status - 100 on error
+  int end(int mode, int M, int N, int K, int lda, int ldb, int ldc) {
+    if (ph.empty()) return -1;
+    if (ph.size() > 32 || (int)calls.size() >= kQrGemmSlots) { set_error("tn_qr: too many blocks / products in the Q formation"); return -100 + TN_ERR_INVALID; }
+    Call c;
+    c.L = GemmLaunch{mode, M, N, K, 1, lda, ldb, ldc, (int)ph.size(), (int)lh.size(), 1, 1};
+    const int st = gemm_plan_schedule(c.L, ph.data(), lh.data(), nullptr, nullptr, &c.S);
+    if (st != TN_OK) return -100 + st;
+    const size_t base = calls.size() * slot_bytes;
+    host.resize(base + slot_bytes, 0);
+    memcpy(host.data() + base, ph.data(), sizeof(ProblemDev) * ph.size());
+    memcpy(host.data() + base + link_off, lh.data(), sizeof(LinkDev) * lh.size());
+    calls.push_back(c);
+    return (int)calls.size() - 1;
+  }
+  int upload(cudaStream_t stream) {
+    if (host.empty()) return TN_OK;
+    TN_CUDA(cudaMemcpyAsync(dev, host.data(), host.size(), cudaMemcpyHostToDevice, stream));
+    return TN_OK;
+  }
+  int launch(int i, cudaStream_t stream) {
+    if (i < 0) return TN_OK;
+    const Call& c = calls[(size_t)i];
+    return gemm_launch(c.L, c.S, reinterpret_cast<const ProblemDev*>(dev + (size_t)i * slot_bytes),
+                       reinterpret_cast<const LinkDev*>(dev + (size_t)i * slot_bytes + link_off), nullptr, nullptr, 1.0, stream);
   }
 };
 
@@ -899,40 +937,49 @@ static int form_q_compact_wy(double* W, int ld, int m, int k, const double* tau,
   const int kp = qr_kp(k);
   const int ns = qr_gram_split(m, k);
   const size_t kk = (size_t)kp * kp;
-  int slot = 0;
-  auto next_slot = [&]() { return static_cast<void*>(slots + (size_t)(slot++) * qr_gemm_slot_bytes()); };
-  qr_make_v_kernel<<<grid_for((long long)k * k), 256, 0, stream>>>(W, ld, k, tau);
-  TN_LAUNCHED();
-  {  // partial Gram matrices over row ranges of V
-    QrGemmCall g;
-    const int rows_per = m / ns;
-    for (int i = 0; i < ns; ++i) g.add(W + (size_t)i * rows_per * ld, W + (size_t)i * rows_per * ld, Gp + i * kk, 1.0, 0);
-    TN_CHECK(g.run(TN_TN, k, k, rows_per, ld, ld, kp, next_slot(), stream));
-  }
-  qr_build_s_kernel<<<grid_for((long long)kk), 256, 0, stream>>>(Gp, ns, kk, S, Tf, Tall, kp, k);
-  TN_LAUNCHED();
+  QrGemmBatch gb(slots);
+#define TN_QR_END(var, ...)                          \
+  const int var = gb.end(__VA_ARGS__);               \
+  if (var <= -100) return var + 100;
+  gb.begin();   // partial Gram matrices over row ranges of V
+  const int rows_per = m / ns;
+  for (int i = 0; i < ns; ++i) gb.add(W + (size_t)i * rows_per * ld, W + (size_t)i * rows_per * ld, Gp + i * kk, 1.0, 0);
+  TN_QR_END(c_gram, TN_TN, k, k, rows_per, ld, ld, kp);
+  std::vector<int> c_levels;
   for (int sz = QNB; sz < kp; sz *= 2) {
-    QrGemmCall y, x;
+    gb.begin();
     for (int a0 = 0; a0 + sz < k; a0 += 2 * sz) {
       const int d0 = a0 + sz;
-      y.add(S + (size_t)a0 * kp + d0, Tf + (size_t)d0 * kp + d0, Y + (size_t)a0 * kp + d0, 1.0, 0);       // Y = B D^-1
-      x.add(Tf + (size_t)a0 * kp + a0, Y + (size_t)a0 * kp + d0, Tf + (size_t)a0 * kp + d0, -1.0, 0);     // -A^-1 Y
+      gb.add(S + (size_t)a0 * kp + d0, Tf + (size_t)d0 * kp + d0, Y + (size_t)a0 * kp + d0, 1.0, 0);       // Y = B D^-1
     }
-    TN_CHECK(y.run(TN_NN, sz, sz, sz, kp, kp, kp, next_slot(), stream));
-    TN_CHECK(x.run(TN_NN, sz, sz, sz, kp, kp, kp, next_slot(), stream));
+    TN_QR_END(cy, TN_NN, sz, sz, sz, kp, kp, kp);
+    gb.begin();
+    for (int a0 = 0; a0 + sz < k; a0 += 2 * sz) {
+      const int d0 = a0 + sz;
+      gb.add(Tf + (size_t)a0 * kp + a0, Y + (size_t)a0 * kp + d0, Tf + (size_t)a0 * kp + d0, -1.0, 0);     // -A^-1 Y
+    }
+    TN_QR_END(cx, TN_NN, sz, sz, sz, kp, kp, kp);
+    c_levels.push_back(cy);
+    c_levels.push_back(cx);
   }
-  {  // Y = T V1^T (k x k), V1 = leading k x k block of V
-    QrGemmCall g;
-    g.add(Tf, W, Y, 1.0, 0);
-    TN_CHECK(g.run(TN_NT, k, k, k, kp, ld, kp, next_slot(), stream));
-  }
+  gb.begin();   // Y = T V1^T (k x k), V1 = leading k x k block of V
+  gb.add(Tf, W, Y, 1.0, 0);
+  TN_QR_END(c_tv, TN_NT, k, k, k, kp, ld, kp);
+  gb.begin();
+  gb.add(W, Y, Qdst, -1.0, 1);
+  TN_QR_END(c_q, TN_NN, m, k, k, ld, kp, k);
+#undef TN_QR_END
+  TN_CHECK(gb.upload(stream));
+  qr_make_v_kernel<<<grid_for((long long)k * k), 256, 0, stream>>>(W, ld, k, tau);
+  TN_LAUNCHED();
+  TN_CHECK(gb.launch(c_gram, stream));
+  qr_build_s_kernel<<<grid_for((long long)kk), 256, 0, stream>>>(Gp, ns, kk, S, Tf, Tall, kp, k);
+  TN_LAUNCHED();
+  for (int c : c_levels) TN_CHECK(gb.launch(c, stream));
+  TN_CHECK(gb.launch(c_tv, stream));
   qr_eye_kernel<<<grid_for((long long)m * k), 256, 0, stream>>>(Qdst, m, k);
   TN_LAUNCHED();
-  {
-    QrGemmCall g;
-    g.add(W, Y, Qdst, -1.0, 1);
-    TN_CHECK(g.run(TN_NN, m, k, k, ld, kp, k, next_slot(), stream));
-  }
+  TN_CHECK(gb.launch(c_q, stream));
   return TN_OK;
 }
 
