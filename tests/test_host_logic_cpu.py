@@ -585,3 +585,37 @@ def test_eigs_fh_host_logic(cpu_be):
     lm, v, info = eigs_fh(lambda x: H @ x.numpy(), d, n=1, which='lm')
     assert abs(abs(lm[0]) - np.abs(w).max()) < 1e-7
     assert set(info) >= {'it_time', 'error'}
+
+
+def test_sharded_observables_partition_covers_every_term_once(cpu_be):
+    """envs.expect_products with a communicator: every rank contracts a block of leading sites and the all-reduce of the value
+    vectors completes the result.  The ranks are simulated one after the other (the all-reduce of the stand-in communicator does
+    nothing), so the partial vectors must have disjoint supports and add up to the unsharded values, for every world size."""
+    from tnalg_b200 import envs
+    from tnalg_b200.MPSClass import MpsOpenBoundaryClass
+    from tnalg_b200 import Parameters as Pm
+    para = Pm.generate_parameters_dmrg('square')
+    para.update(square_width=3, square_height=2, chi=8, op=para['op'][:6])
+    para = Pm.make_consistent_parameter_dmrg(para)
+    np.random.seed(5)
+    A = MpsOpenBoundaryClass(para['l'], para['d'], para['chi'], operators=para['op'], is_save_op=True, eig_way=1)
+    A.correct_orthogonal_center(2)
+    index2 = np.asarray(para['index2'], dtype=int)
+    terms = [tuple(sorted(((int(r[0]), int(r[2])), (int(r[1]), int(r[3]))))) for r in index2]
+    terms += [((i, 1),) for i in range(para['l'])] + [((i, 3),) for i in range(para['l'])]
+    ops_real = [np.real(np.asarray(o)).astype(float) for o in para['op']]
+    want = envs.expect_products(cpu_be, A.mps, A.center, ops_real, terms)
+
+    class OneRank:
+        def __init__(self, rank, world):
+            self.rank, self.world = rank, world
+
+        def allreduce(self, t):
+            return t
+
+    for world in (2, 3, 8):
+        parts = [envs.expect_products(cpu_be, A.mps, A.center, ops_real, terms, comm=OneRank(r, world), min_terms=1)
+                 for r in range(world)]
+        support = np.sum([np.asarray(p) != 0 for p in parts], axis=0)
+        assert support.max() <= 1
+        assert np.abs(np.sum(parts, axis=0) - want).max() < 1e-13
