@@ -619,3 +619,50 @@ def test_sharded_observables_partition_covers_every_term_once(cpu_be):
         support = np.sum([np.asarray(p) != 0 for p in parts], axis=0)
         assert support.max() <= 1
         assert np.abs(np.sum(parts, axis=0) - want).max() < 1e-13
+
+
+def test_sharded_bond_move_places_every_block_once(cpu_be):
+    """EnvCache._env_update with a communicator: the outgoing blocks are dealt round-robin (heaviest first), every rank writes its
+    own into its rows of one buffer and an in-place all-gather completes it.  Ranks are simulated one after the other with an
+    all-gather that does nothing: every block must be produced by exactly one rank, equal to the unsharded result, and land in
+    the row all ranks agree on."""
+    import torch
+    from tnalg_b200 import envs
+    rng = np.random.RandomState(11)
+    a, d, b = 6, 2, 5
+    T = torch.from_numpy(rng.randn(a, d, b))
+    sz = np.array([[0.5, 0.0], [0.0, -0.5]])
+    sp = np.array([[0.0, 1.0], [0.0, 0.0]])
+    E = [torch.from_numpy(rng.randn(a, a)) for _ in range(4)]
+    outputs = [[(E[0], None), (E[1], sz), (None, sz)], [(None, sp)], [(E[2], None)], [(E[3], sp)], [(None, sz)], [(E[1], None)], [(E[0], sp)]]
+    want = cpu_be.env_update(0, T, outputs)
+
+    class OneRank:
+        def __init__(self, rank, world):
+            self.rank, self.world = rank, world
+
+        def allgather_inplace(self, buf):
+            self.buf = buf
+            return buf
+
+    terms = envs.TermTable(np.zeros((0, 2), dtype=int), np.array([[0, 1, 1, 1]]), np.zeros((0, 1)), np.ones((1, 1)), [np.eye(2), sz, sp, sz], 1e-12)
+    for world in (2, 3, 8):
+        got = [None] * len(outputs)
+        rows = None
+        for r in range(world):
+            cache = envs.EnvCache(cpu_be, terms, 2)
+            cache.shard_min_dim = 1
+            cache.comm = OneRank(r, world)
+            res = cache._env_update(0, T, outputs)
+            per = (len(outputs) + world - 1) // world
+            assert cache.comm.buf.shape == (world * per, b, b)
+            # the row of every block inside the buffer is the same on all ranks
+            place = [int((blk.data_ptr() - cache.comm.buf.data_ptr()) // (8 * b * b)) for blk in res]
+            rows = place if rows is None else rows
+            assert place == rows and sorted(place) == sorted(set(place))
+            for j, blk in enumerate(res):
+                if r * per <= place[j] < (r + 1) * per:      # this rank's own rows
+                    assert got[j] is None
+                    got[j] = blk.clone()
+        for j in range(len(outputs)):
+            assert got[j] is not None and np.abs(got[j].numpy() - want[j].numpy()).max() < 1e-14
