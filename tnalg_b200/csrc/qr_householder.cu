@@ -7,15 +7,19 @@
 //   the signs of its rows whenever A has full column rank.
 //
 // Structure (right-looking, panel width 32):
-//   qr_panel_kernel   one thread-block CLUSTER per panel.  The panel rows are spread over the CTAs of the cluster and stay in
-//                     shared memory for all 32 columns.  Per column ONE cluster-wide reduction (distributed shared memory +
-//                     barrier.cluster) yields the whole row  g_k = sum_{r>=j} P[r,j] P[r,k]  of the panel Gram matrix, from
-//                     which the column norm (k = j), the reflector products v^T a_k (k > j) and the entries V_k^T v_j of the
-//                     compact-WY factor T (k < j) all follow:  y_k = (g_k - beta P[j,k]) / (alpha - beta).
-//                     Latency per column = one CTA barrier + one cluster barrier (~0.5 us), not a chain of launches.
+//   qr_panel_kernel   one thread-block CLUSTER per panel (128 rows per CTA up to 1024 rows, 256 at 2048).  The panel lives in
+//                     REGISTERS (thread = (row slot, column)).  Per column ONE reduction -- warp partials through shared memory,
+//                     CTA partials through asynchronous remote stores that count on the destination's mbarrier -- yields the
+//                     whole row  g_k = sum_{r>=j} P[r,j] P[r,k]  of the panel Gram matrix, from which the column norm (k = j), the
+//                     reflector products v^T a_k (k > j) and the entries V_k^T v_j of the compact-WY factor T (k < j) all follow:
+//                     y_k = (g_k - beta P[j,k]) / (alpha - beta).  Before factoring, the kernel applies the block reflector of the
+//                     PREVIOUS panel to its own columns in registers (fused look-ahead), so no launch sits between two panels.
 //   qr_apply_kernel   C <- (1 - V op(T) V^T) C on a strip of 32 columns per cluster (the CTAs split the rows) with FP64
 //                     tensor-core MMAs (DMMA.8x8x4): W = V^T C (partial tiles meet in distributed shared memory, summed in
-//                     CTA order), W <- op(T) W, C -= V W.  Used for the trailing update (op(T) = T^T) and for forming Q (op(T) = T, panels in reverse).
+//                     CTA order), W <- op(T) W, C -= V W.  Carries the wide trailing update (op(T) = T^T) on a side stream while
+//                     the next panel is factored.
+//   form_q_compact_wy Q = [1; 0] - V (T V1^T) with T^-1 = diag(1 / tau) + striu(V^T V): deterministic chain GEMMs plus a
+//                     recursive-doubling inverse over the 32 x 32 diagonal blocks (short matrices form Q by reverse applies).
 // No atomics anywhere: results are bit-reproducible (replicas on several GPUs stay identical).
 #include <cooperative_groups.h>
 
